@@ -1,0 +1,255 @@
+/*
+ * tadev.h — C ABI of libtadev, the B200 (sm_100a) contraction engine that sits behind
+ * TiledArray's tile plug-in and evaluator plug-in interfaces.
+ *
+ * Conventions (all entry points):
+ *   - return int status: 0 = TADEV_OK, otherwise a TADEV_E* code; never throw.
+ *     tadev_last_error() returns a thread-local message for the last failure.
+ *   - every device operation takes an explicit cudaStream_t (passed as void*), is
+ *     asynchronous with respect to the host, and is thread-safe for concurrent calls on
+ *     distinct streams (the contract TiledArray's MADWorld task threads rely on,
+ *     reference: src/TiledArray/external/device.h:847-907).
+ *   - tiles are dense row-major FP64 blocks living in device memory (NOT unified memory).
+ *   - pointers named d_* are device pointers, h_* are host pointers.
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns
+ *     TADEV_ENODEVICE. Pure host-logic entries (ProcGrid, pmap, permutation planning,
+ *     SUMMA schedule) work without a device; they are marked [host].
+ *
+ * Each entry cites the reference interface (file:line under ValeevGroup/tiledarray) it replaces.
+ */
+#ifndef TADEV_H_INCLUDED
+#define TADEV_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TADEV_OK 0
+#define TADEV_EINVAL 1    /* bad argument (the analogue of TA_ASSERT -> TiledArray::Exception) */
+#define TADEV_ECUDA 2     /* CUDA runtime error (reference: DeviceSafeCall, external/device.h:71-97) */
+#define TADEV_ENODEVICE 3 /* no CUDA device: there is deliberately no CPU path */
+#define TADEV_ENCCL 4     /* NCCL error */
+#define TADEV_ENOMEM 5
+
+#define TADEV_OP_N 0 /* blas::Op::NoTrans  (math/blas.h) */
+#define TADEV_OP_T 1 /* blas::Op::Trans */
+
+typedef struct tadev_ctx tadev_ctx;
+typedef void* tadev_stream; /* cudaStream_t */
+
+const char* tadev_last_error(void);
+const char* tadev_version(void);
+
+/* ---- context, streams, memory ------------------------------------------------------
+ * replaces device::Env (external/device.h:536-605: rank->device map, N non-blocking
+ * streams, Umpire pools) and BLASQueuePool (device/blas.h:66-76). */
+int tadev_init(int device, size_t pool_bytes, tadev_ctx** out);
+int tadev_finalize(tadev_ctx* ctx);
+int tadev_device_count(int* n);
+/* number of compute streams owned by the ctx (TA_DEVICE_NUM_STREAMS analogue, default 3) */
+int tadev_num_streams(tadev_ctx* ctx, int* n);
+int tadev_get_stream(tadev_ctx* ctx, int i, tadev_stream* out);
+/* stream_for(range) analogue (external/device.h:899-907): stream = ordinal % nstreams */
+int tadev_stream_for(tadev_ctx* ctx, uint64_t ordinal, tadev_stream* out);
+int tadev_stream_sync(tadev_ctx* ctx, tadev_stream s);
+int tadev_alloc(tadev_ctx* ctx, size_t bytes, void** d_ptr, tadev_stream s);
+int tadev_free(tadev_ctx* ctx, void* d_ptr, tadev_stream s);
+int tadev_memcpy_h2d(tadev_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, tadev_stream s);
+int tadev_memcpy_d2h(tadev_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, tadev_stream s);
+int tadev_memset(tadev_ctx* ctx, void* d_dst, int byte, size_t bytes, tadev_stream s);
+/* CUDA-event timing on a caller stream (bench.py times on the launching stream) */
+int tadev_event_create(tadev_ctx* ctx, void** ev);
+int tadev_event_record(tadev_ctx* ctx, void* ev, tadev_stream s);
+int tadev_event_elapsed_ms(tadev_ctx* ctx, void* ev_start, void* ev_stop, float* ms); /* syncs on ev_stop */
+int tadev_event_destroy(tadev_ctx* ctx, void* ev);
+int tadev_host_alloc(size_t bytes, void** h_ptr); /* pinned */
+int tadev_host_free(void* h_ptr);
+
+/* ---- tile GEMM -------------------------------------------------------------------------
+ * replaces Tensor::gemm (tensor/tensor.h:3132-3219) -> detail::gemm (tensor/kernels.h:92-231)
+ * -> math::blas::gemm (math/blas.h:171-177) and device::btas::gemm (device/btas.h:52-222),
+ * and folds ContractReduce's pair-accumulate + add_to merge (tile_op/contract_reduce.h:386-453)
+ * into one launch.
+ *
+ * A task is one (left tile, right tile) product contributing to a result tile:
+ *   C[m x n] (+)= alpha * op(A) * op(B), all row-major, natural leading dimensions
+ *   (lda = k|m, ldb = n|k, ldc = n, exactly tensor/kernels.h:146-158).
+ * Tasks are grouped by result tile: group g owns tasks [task_begin[g], task_begin[g+1]) which
+ * are accumulated IN REGISTERS in list order and written to C once; if accumulate[g] != 0 the
+ * previous contents of C are added (beta = 1), otherwise C is overwritten (beta = 0).       */
+typedef struct {
+  const double* A; /* device */
+  const double* B; /* device */
+  int32_t k;       /* contracted (fused inner) extent of this pair */
+  int32_t reserved;
+} tadev_gemm_task;
+
+typedef struct {
+  double* C;          /* device, m x n row-major */
+  int32_t m, n;       /* fused outer extents */
+  int32_t task_begin; /* first task of this group */
+  int32_t task_end;   /* one past the last task */
+  int32_t accumulate; /* 0: C = alpha*sum ; 1: C += alpha*sum */
+  int32_t reserved;
+} tadev_gemm_group;
+
+/* h_groups/h_tasks are HOST arrays; the call copies them to the device on `s` (staging is
+ * owned by the ctx) and launches one grouped DMMA kernel. */
+int tadev_gemm_grouped_f64(tadev_ctx* ctx, tadev_stream s, int opA, int opB, double alpha,
+                           const tadev_gemm_group* h_groups, int ngroups,
+                           const tadev_gemm_task* h_tasks, int ntasks);
+/* Same, but descriptors already live in device memory (used by the SUMMA driver, whose
+ * per-step lists are produced on the device by tadev_build_pairlist). */
+int tadev_gemm_grouped_f64_dev(tadev_ctx* ctx, tadev_stream s, int opA, int opB, double alpha,
+                               const tadev_gemm_group* d_groups, int ngroups,
+                               const tadev_gemm_task* d_tasks, const int32_t* d_tile_prefix,
+                               int total_cta_tiles);
+/* Single-pair convenience with the exact reference signature semantics:
+ *   beta == 0: result allocated/overwritten ("gemm(left,right,factor,helper)", tile_interface.h:803)
+ *   beta == 1: accumulate ("gemm(result,left,right,factor,helper)", tile_interface.h:825). */
+int tadev_gemm_f64(tadev_ctx* ctx, tadev_stream s, int opA, int opB, int m, int n, int k,
+                   double alpha, const double* d_A, const double* d_B, double beta, double* d_C);
+
+/* ---- tile permutation --------------------------------------------------------------------
+ * replaces detail::permute (tensor/permute.h:118-209) and librett_permute
+ * (external/librett.h:81-111). perm is in TiledArray image form (permutation.h:69-79):
+ *   out.extent[perm[i]] = extent[i];  out[perm applied to idx] = in[idx].
+ * elem_bytes in {4, 8, 16}. */
+int tadev_permute(tadev_ctx* ctx, tadev_stream s, int rank, const int64_t* extent,
+                  const int32_t* perm, int elem_bytes, const void* d_in, void* d_out);
+/* result(+)= arg: ContractReduce partial-result merge (contract_reduce.h:397-398; GPU ref
+ * device/btas_um_tensor.h:377-384 axpy). */
+int tadev_add_to_f64(tadev_ctx* ctx, tadev_stream s, size_t n, double* d_result, const double* d_arg);
+int tadev_scale_f64(tadev_ctx* ctx, tadev_stream s, size_t n, double* d_x, double factor);
+/* squared Frobenius norms of `ntiles` tiles (for truncate / true result shapes,
+ * dist_array.h:1553). d_ptrs/d_sizes are device arrays; out is a device array of doubles. */
+int tadev_tile_sqnorms_f64(tadev_ctx* ctx, tadev_stream s, int ntiles, const double* const* d_ptrs,
+                           const int64_t* d_sizes, double* d_out);
+/* counter-based uniform(-1,1) fill keyed by (seed, global element offset): synthetic inputs
+ *  and on-the-fly tile generation for tensors that do not fit in HBM. */
+int tadev_fill_uniform_f64(tadev_ctx* ctx, tadev_stream s, double* d_x, size_t n, uint64_t seed,
+                           uint64_t offset);
+
+/* ---- SparseShape screening (FP32, bit-exact vs oracle) ----------------------------------
+ * replaces SparseShape<float>::scale_tile_norms (sparse_shape.h:149-217), gemm (:1589-1681),
+ * perm (:1222), mask (:653-676), is_zero (:495-498). All arrays are device arrays. */
+/* norms[i] *= left[i / nright] * right[i % nright]; hard-zero below threshold; count zeros.
+ * rank-1 shapes pass nright = 0: norms[i] /= left[i] (the reference's divide branch).     */
+int tadev_shape_scale_f32(tadev_ctx* ctx, tadev_stream s, float* d_norms, const float* d_left,
+                          int64_t nleft, const float* d_right, int64_t nright, float threshold,
+                          uint64_t* d_nzero);
+/* out[m,n] = |factor| * sum_k (a[m,k]*ksz[k]) * (b[k,n]*ksz[k]), sequential k, fp32 FMA;
+ * values < threshold are hard-zeroed and counted. Kt == 0: outer product a[m]*b[n]*|factor|. */
+int tadev_shape_gemm_f32(tadev_ctx* ctx, tadev_stream s, int Mt, int Nt, int Kt, const float* d_a,
+                         const float* d_b, const float* d_ksz, float abs_factor, float threshold,
+                         float* d_out, uint64_t* d_nzero);
+int tadev_shape_mask_f32(tadev_ctx* ctx, tadev_stream s, int64_t n, float* d_norms,
+                         const float* d_mask, float thr_this, float thr_mask, uint64_t* d_nzero);
+
+/* ---- tile-pair list of one SUMMA step ---------------------------------------------------
+ * replaces Summa::contract (dist_eval/contraction_eval.h:1311-1384) + get_col/get_row
+ * (:655-676): for step k on grid position (r,c) of a Pr x Pc grid, emit, in (i,j) row-major
+ * order, the pairs {(i,j): i%Pr==r, j%Pc==c, a[i,k]>=thr, b[k,j]>=thr, c[i,j]>=thr}.
+ * NULL norm arrays mean dense. Output is a device int2 list + device count. */
+int tadev_build_pairlist(tadev_ctx* ctx, tadev_stream s, int k, int Pr, int Pc, int r, int c, int Mt,
+                         int Nt, int Kt, const float* d_a, const float* d_b, const float* d_c,
+                         float threshold, int32_t* d_pair_i, int32_t* d_pair_j, int32_t* d_npairs);
+
+/* ---- [host] process grid / pmap / permutation planning ------------------------------------ */
+/* ProcGrid (proc_grid.h:97-260): grid dims + this rank's coordinates and local counts.
+ * rank >= proc_rows*proc_cols  =>  rank_row = rank_col = -1 and local counts 0. */
+typedef struct {
+  int32_t proc_rows, proc_cols, proc_size;
+  int32_t rank_row, rank_col;
+  int64_t local_rows, local_cols, local_size;
+} tadev_proc_grid;
+int tadev_proc_grid_make(int rank, int nprocs, int64_t rows, int64_t cols, int64_t row_size,
+                         int64_t col_size, tadev_proc_grid* out);
+/* CyclicPmap::owner (pmap/cyclic_pmap.h:123-134) */
+int tadev_cyclic_owner(int64_t tile, int64_t cols, int proc_rows, int proc_cols, int* owner);
+
+/* GEMMPermutationOptimizer (expressions/permopt.h:254-376) + the result permutation of
+ * ContEngine::init_struct (expressions/cont_engine.h:354-529). Index lists are comma-separated
+ * strings ("i,k,a,c"). Output permutations are in image form; perm_*[0] == -1 means identity. */
+typedef struct {
+  int32_t left_rank, right_rank, result_rank, inner_rank;
+  int32_t opA, opB;          /* TADEV_OP_* handed to the tile GEMM */
+  int32_t left_permtype;     /* 1 identity, 2 matrix_transpose, 3 general (permopt.h:39) */
+  int32_t right_permtype;
+  int32_t perm_left[16];     /* explicit argument-tile permutation (general case) */
+  int32_t perm_right[16];
+  int32_t perm_result[16];   /* GEMM result order -> target order */
+  char left_target[256];     /* target index lists, comma separated */
+  char right_target[256];
+  char result_gemm[256];
+} tadev_contraction_plan;
+int tadev_plan_contraction(const char* target, const char* left, const char* right,
+                           tadev_contraction_plan* out);
+
+/* ---- multi-GPU: communicators + SUMMA driver ------------------------------------------------
+ * replaces detail::Summa (dist_eval/contraction_eval.h:55-2027) and its world.gop.bcast
+ * row/column tile broadcasts (:712,:849,:903) by NCCL broadcasts of packed panels on
+ * row/column communicators of a Pr x Pc grid (one process per GPU). */
+int tadev_comm_unique_id(void* out128);
+int tadev_comm_init(tadev_ctx* ctx, const void* unique_id128, int rank, int nranks, int Pr, int Pc);
+int tadev_comm_destroy(tadev_ctx* ctx);
+/* which=0: row communicator (A panels), which=1: column communicator (B panels). */
+int tadev_bcast_panel(tadev_ctx* ctx, tadev_stream s, int which, int root, void* d_buf, size_t bytes);
+
+typedef struct {
+  int32_t Mt, Nt, Kt;       /* fused tile-grid extents of C (Mt x Nt) and the contraction (Kt) */
+  const int64_t* m_ext;     /* [Mt] fused element extent of each tile row      (host) */
+  const int64_t* n_ext;     /* [Nt]                                              (host) */
+  const int64_t* k_ext;     /* [Kt]                                              (host) */
+  int32_t opA, opB;         /* storage of argument tiles: N: A(i,k) is m x k; T: k x m */
+  double alpha;
+  /* replicated scaled norms (host, row-major [Mt,Kt], [Kt,Nt], [Mt,Nt]); NULL = dense */
+  const float* a_norms;
+  const float* b_norms;
+  const float* c_norms;
+  float threshold;
+  /* device pointers (host arrays of device pointers, full tile grids, row-major ordinals).
+   * Only entries owned by this rank under the cyclic maps (proc_grid.h:566-597) are read:
+   *   A(i,k): (i%Pr, k%Pc)   B(k,j): (k%Pr, j%Pc)   C(i,j): (i%Pr, j%Pc). */
+  const double* const* a_tiles;
+  const double* const* b_tiles;
+  double* const* c_tiles;
+  int32_t accumulate;       /* 0: C = alpha*A*B ; 1: C += */
+  int32_t depth;            /* SUMMA pipeline depth (0 = reference default, :1925-1977) */
+  int32_t steps_per_launch; /* K steps fused into one grouped-GEMM launch (0 = auto) */
+  int32_t reserved;
+} tadev_summa_plan;
+
+typedef struct {
+  int64_t nsteps, nsteps_skipped, npairs, nlaunches;
+  double flops;       /* 2*m*n*k summed over executed pairs on this rank */
+  int64_t bcast_bytes; /* bytes this rank sent or received in panel broadcasts */
+  float device_ms;    /* CUDA-event time of the whole contraction on this rank */
+} tadev_summa_stats;
+
+int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_stats* stats);
+
+/* [host] the schedule the driver will execute, for inspection/tests: per step the root grid
+ * column/row and the pair list of this rank. Arrays are caller-allocated with capacities.
+ * pairs are (i,j) global tile coordinates in row-major order. */
+int tadev_summa_schedule(int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt, const float* a_norms,
+                         const float* b_norms, const float* c_norms, float threshold,
+                         int32_t* step_k, int32_t* step_pair_begin, int32_t* nsteps_out,
+                         int32_t* pair_i, int32_t* pair_j, int64_t pair_capacity, int64_t* npairs_out);
+
+/* ---- measurement helpers -------------------------------------------------------------------
+ * Register-resident DMMA / DFMA issue-rate probes: the FP64 roofline denominator is not in
+ * MEASURED_PEAKS.json and must be measured on the box. Returns TFLOP/s. */
+int tadev_probe_fp64_peak(tadev_ctx* ctx, int kind /*0 dmma, 1 dfma, 2 both*/, int iters,
+                          double* tflops, float* ms);
+int tadev_probe_copy_gbs(tadev_ctx* ctx, size_t bytes, int iters, double* gbs);
+/* number of kernels this library launched since init (bench.py's gpu_launches) */
+int tadev_launch_count(tadev_ctx* ctx, int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TADEV_H_INCLUDED */

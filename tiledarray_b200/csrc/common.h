@@ -1,0 +1,75 @@
+// common.h — internal declarations shared by the libtadev translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/tadev.h"
+
+struct ncclComm;
+
+void tadev_set_error(const char* fmt, ...);
+
+#define TADEV_CHECK_CUDA(expr)                                                            \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      tadev_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return TADEV_ECUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define TADEV_REQUIRE(cond, ...)   \
+  do {                             \
+    if (!(cond)) {                 \
+      tadev_set_error(__VA_ARGS__); \
+      return TADEV_EINVAL;         \
+    }                              \
+  } while (0)
+
+// A grow-only device/pinned staging buffer pair used to ship descriptor lists to the device.
+// One ring per stream slot so concurrent callers on distinct streams never share a buffer.
+struct StagingRing {
+  static constexpr int kSlots = 4;
+  void* h[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  void* d[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kSlots] = {0, 0, 0, 0};
+  cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  int next = 0;
+};
+
+struct tadev_ctx {
+  int device = -1;
+  int num_sms = 0;
+  cudaMemPool_t pool = nullptr;
+  std::vector<cudaStream_t> streams;  // compute streams (non-blocking)
+  cudaStream_t comm_stream[2] = {nullptr, nullptr};  // row / column panel broadcasts (high priority)
+  std::atomic<int64_t> launches{0};
+  std::mutex mu;  // guards staging rings
+  std::vector<std::pair<cudaStream_t, StagingRing>> staging;
+  // communicators
+  ncclComm* world = nullptr;
+  ncclComm* row_comm = nullptr;  // ranks sharing my grid row   (A column-panels travel here)
+  ncclComm* col_comm = nullptr;  // ranks sharing my grid column (B row-panels travel here)
+  int rank = 0, nranks = 1, Pr = 1, Pc = 1, my_r = 0, my_c = 0;
+};
+
+// Obtain a staging slot of at least `bytes` for stream s. Returns host + device pointers; the
+// caller memcpyAsync's h->d on s and then records `*done` on s after the consuming kernel.
+int tadev_stage(tadev_ctx* ctx, cudaStream_t s, size_t bytes, void** h, void** d, cudaEvent_t* done);
+
+// kernels' internal launchers (device-resident descriptors)
+int launch_gemm_grouped_f64(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, double alpha,
+                            const tadev_gemm_group* d_groups, int ngroups, const tadev_gemm_task* d_tasks,
+                            const int32_t* d_tile_prefix, int total_cta_tiles, bool aligned16);
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// CTA tile of the grouped DGEMM kernel (shared by host tile counting and the kernel)
+constexpr int kGemmBM = 128;
+constexpr int kGemmBN = 128;

@@ -1,0 +1,328 @@
+// permute.cu — out-of-place tile permutation, HBM-bandwidth bound.
+//
+// Replaces detail::permute (reference: src/TiledArray/tensor/permute.h:118-209; dimension
+// fusion follows the idea of fuse_dimensions, :51-94) and the per-call plan/execute/destroy of
+// LibreTT (external/librett.h:81-111). Semantics are TiledArray's image convention
+// (permutation.h:69-79): out.extent[perm[i]] = in.extent[i] and out[p(idx)] = in[idx].
+//
+// Planning is a few integer ops on the host per call (no plan objects): drop unit extents, fuse
+// input modes that stay adjacent and ordered in the output, then pick one of three kernels
+//   1. identity after fusion           -> cudaMemcpyAsync D2D
+//   2. last mode stays last            -> row-copy kernel (16-byte vectorised when aligned)
+//   3. otherwise                       -> shared-memory tiled transpose over (a, b) where a is the
+//      input-fastest mode and b the output-fastest mode; global reads are coalesced along a,
+//      global writes along b, smem rows are padded by one element (conflict-free both ways).
+#include "common.h"
+
+namespace {
+
+constexpr int MAXR = 8;
+
+struct PermParams {
+  int R;                 // reduced rank
+  int64_t ext[MAXR];     // input extents (reduced)
+  int64_t sin[MAXR];     // input strides  (elements)
+  int64_t sout[MAXR];    // output stride of the output mode each input mode maps to
+  int a, b;              // input-fastest mode (R-1) and output-fastest mode (as input-mode index)
+  int TA, TB;            // tile extents along a and b (powers of two)
+  int64_t nTa, nTb;      // tiles along a and b
+  int nother;            // number of remaining modes
+  int other[MAXR];       // their input-mode indices, fastest varying first
+  int64_t total;         // total elements
+  // row-copy
+  int64_t row_len;       // elements per preserved row (already divided by vec)
+  int64_t nrows;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_tiled_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                              PermParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  const int TA = p.TA, TB = p.TB;
+  const int ldt = TA + 1;
+  int64_t bid = blockIdx.x;
+  const int64_t ta = bid % p.nTa; bid /= p.nTa;
+  const int64_t tb = bid % p.nTb; bid /= p.nTb;
+  int64_t base_in = 0, base_out = 0;
+  for (int d = 0; d < p.nother; ++d) {
+    const int m = p.other[d];
+    const int64_t i = bid % p.ext[m];
+    bid /= p.ext[m];
+    base_in += i * p.sin[m];
+    base_out += i * p.sout[m];
+  }
+  const int64_t a0 = ta * TA, b0 = tb * TB;
+  const int64_t ea = p.ext[p.a], eb = p.ext[p.b];
+  const int64_t sin_b = p.sin[p.b], sout_a = p.sout[p.a];
+  const int la = 31 - __clz(TA);  // log2
+  const int lb = 31 - __clz(TB);
+  const int n = TA * TB;
+  // read: consecutive threads walk the input-fastest mode a
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < n; idx += 256) {
+    const int ia = idx & (TA - 1), ib = idx >> la;
+    if (a0 + ia < ea && b0 + ib < eb) tile[ib * ldt + ia] = in[base_in + (b0 + ib) * sin_b + (a0 + ia)];
+  }
+  __syncthreads();
+  // write: consecutive threads walk the output-fastest mode b
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < n; idx += 256) {
+    const int ib = idx & (TB - 1), ia = idx >> lb;
+    if (a0 + ia < ea && b0 + ib < eb) out[base_out + (a0 + ia) * sout_a + (b0 + ib)] = tile[ib * ldt + ia];
+  }
+}
+
+// Rows (the preserved, contiguous last mode) are copied whole; V is the vector type.
+template <typename V>
+__global__ void __launch_bounds__(256) rowcopy_kernel(const V* __restrict__ in, V* __restrict__ out, PermParams p) {
+  const int64_t total = p.nrows * p.row_len;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += stride) {
+    int64_t row = q / p.row_len;
+    const int64_t c = q - row * p.row_len;
+    // q enumerates the OUTPUT in order: decompose the output row ordinal into output-mode
+    // indices. other[] lists the non-row modes by increasing output stride.
+    int64_t off_in = 0;
+    for (int d = 0; d < p.nother; ++d) {
+      const int m = p.other[d];
+      const int64_t i = row % p.ext[m];
+      row /= p.ext[m];
+      off_in += i * p.sin[m];
+    }
+    out[q] = in[off_in + c];  // sin[] pre-divided by the vector width for the row mode
+  }
+}
+
+int64_t pow2_ceil(int64_t x) {
+  int64_t r = 1;
+  while (r < x) r *= 2;
+  return r;
+}
+
+template <typename T>
+int launch_tiled(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const void* in, void* out) {
+  int64_t blocks = p.nTa * p.nTb;
+  for (int d = 0; d < p.nother; ++d) blocks *= p.ext[p.other[d]];
+  TADEV_REQUIRE(blocks < (1ll << 31), "tadev_permute: tile too large for one launch");
+  const size_t smem = sizeof(T) * (size_t)(p.TA + 1) * p.TB;
+  transpose_tiled_kernel<T><<<(unsigned)blocks, 256, smem, s>>>((const T*)in, (T*)out, p);
+  ctx->launches++;
+  TADEV_CHECK_CUDA(cudaGetLastError());
+  return TADEV_OK;
+}
+
+template <typename V>
+int launch_rowcopy(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const void* in, void* out) {
+  const int64_t total = p.nrows * p.row_len;
+  int64_t blocks = ceil_div64(total, 256 * 4);
+  const int64_t maxb = (int64_t)ctx->num_sms * 32;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  rowcopy_kernel<V><<<(unsigned)blocks, 256, 0, s>>>((const V*)in, (V*)out, p);
+  ctx->launches++;
+  TADEV_CHECK_CUDA(cudaGetLastError());
+  return TADEV_OK;
+}
+
+}  // namespace
+
+extern "C" int tadev_permute(tadev_ctx* ctx, tadev_stream s_, int rank, const int64_t* extent,
+                             const int32_t* perm, int elem_bytes, const void* d_in, void* d_out) {
+  TADEV_REQUIRE(ctx, "tadev_permute: null ctx");
+  TADEV_REQUIRE(rank >= 0 && rank <= 16, "tadev_permute: rank %d unsupported", rank);
+  TADEV_REQUIRE(elem_bytes == 4 || elem_bytes == 8 || elem_bytes == 16, "tadev_permute: elem_bytes %d", elem_bytes);
+  TADEV_REQUIRE(rank == 0 || (extent && perm), "tadev_permute: null extent/perm");
+  cudaStream_t s = (cudaStream_t)s_;
+  // validate the permutation
+  {
+    uint32_t seen = 0;
+    for (int i = 0; i < rank; ++i) {
+      TADEV_REQUIRE(perm[i] >= 0 && perm[i] < rank && !(seen >> perm[i] & 1), "tadev_permute: not a permutation");
+      seen |= 1u << perm[i];
+      TADEV_REQUIRE(extent[i] >= 0, "tadev_permute: negative extent");
+    }
+  }
+  int64_t total = 1;
+  for (int i = 0; i < rank; ++i) total *= extent[i];
+  if (total == 0) return TADEV_OK;
+  TADEV_REQUIRE(d_in && d_out, "tadev_permute: null tile");
+  TADEV_REQUIRE(d_in != d_out, "tadev_permute: in-place permutation is not supported");
+
+  // output strides per output mode
+  int64_t out_ext[16], out_stride[16];
+  for (int i = 0; i < rank; ++i) out_ext[perm[i]] = extent[i];
+  {
+    int64_t st = 1;
+    for (int j = rank - 1; j >= 0; --j) { out_stride[j] = st; st *= out_ext[j]; }
+  }
+  // reduce: drop unit modes, fuse input modes i,i+1 with perm[i+1] == perm[i]+1
+  int R = 0;
+  int64_t ext[16], sout[16];
+  for (int i = 0; i < rank; ++i) {
+    if (extent[i] == 1) continue;
+    ext[R] = extent[i];
+    sout[R] = out_stride[perm[i]];
+    ++R;
+  }
+  // fuse: mode j+1 follows mode j contiguously in the output iff sout[j] == sout[j+1]*ext[j+1]
+  {
+    int W = 0;
+    for (int i = 0; i < R; ++i) {
+      if (W > 0 && sout[W - 1] == sout[i] * ext[i]) {
+        ext[W - 1] *= ext[i];
+        sout[W - 1] = sout[i];
+      } else {
+        ext[W] = ext[i]; sout[W] = sout[i]; ++W;
+      }
+    }
+    R = W;
+  }
+  if (R <= 1) {  // identity
+    TADEV_CHECK_CUDA(cudaMemcpyAsync(d_out, d_in, (size_t)total * elem_bytes, cudaMemcpyDeviceToDevice, s));
+    return TADEV_OK;
+  }
+  TADEV_REQUIRE(R <= MAXR, "tadev_permute: reduced rank %d > %d", R, MAXR);
+  PermParams p{};
+  p.R = R;
+  p.total = total;
+  {
+    int64_t st = 1;
+    for (int i = R - 1; i >= 0; --i) { p.ext[i] = ext[i]; p.sout[i] = sout[i]; p.sin[i] = st; st *= ext[i]; }
+  }
+  if (p.sout[R - 1] == 1) {
+    // last mode preserved: row copy. Enumerate rows in OUTPUT order: sort the other modes by sout.
+    int idx[MAXR], n = 0;
+    for (int i = 0; i < R - 1; ++i) idx[n++] = i;
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j)
+        if (p.sout[idx[j]] < p.sout[idx[i]]) { int tswap = idx[i]; idx[i] = idx[j]; idx[j] = tswap; }
+    p.nother = n;
+    for (int i = 0; i < n; ++i) p.other[i] = idx[i];
+    const int64_t L = p.ext[R - 1];
+    p.nrows = total / L;
+    const int64_t row_bytes = L * elem_bytes;
+    const bool al16 = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
+    if (al16) {
+      const int vec = 16 / elem_bytes;
+      p.row_len = L / vec;
+      for (int i = 0; i < R - 1; ++i) p.sin[i] /= vec;
+      return launch_rowcopy<uint4>(ctx, s, p, d_in, d_out);
+    }
+    p.row_len = L;
+    if (elem_bytes == 4) return launch_rowcopy<uint32_t>(ctx, s, p, d_in, d_out);
+    if (elem_bytes == 8) return launch_rowcopy<uint64_t>(ctx, s, p, d_in, d_out);
+    return launch_rowcopy<uint4>(ctx, s, p, d_in, d_out);
+  }
+  // general: tiled transpose over a = R-1 and b = the mode with sout == 1
+  p.a = R - 1;
+  p.b = -1;
+  for (int i = 0; i < R; ++i)
+    if (p.sout[i] == 1) p.b = i;
+  TADEV_REQUIRE(p.b >= 0 && p.b != p.a, "tadev_permute: internal planning error");
+  // tile: ~2048 elements; give the short mode its full (power-of-two padded) extent
+  int64_t TB = pow2_ceil(p.ext[p.b]); if (TB > 32) TB = 32;
+  int64_t TA = pow2_ceil(p.ext[p.a]); if (TA > 2048 / TB) TA = 2048 / TB;
+  if (TA < 32) { // a is short: widen b instead
+    TB = pow2_ceil(p.ext[p.b]); if (TB > 2048 / TA) TB = 2048 / TA;
+  }
+  p.TA = (int)TA; p.TB = (int)TB;
+  p.nTa = ceil_div64(p.ext[p.a], TA);
+  p.nTb = ceil_div64(p.ext[p.b], TB);
+  p.nother = 0;
+  for (int i = R - 2; i >= 0; --i)
+    if (i != p.b) p.other[p.nother++] = i;
+  if (elem_bytes == 4) return launch_tiled<uint32_t>(ctx, s, p, d_in, d_out);
+  if (elem_bytes == 8) return launch_tiled<uint64_t>(ctx, s, p, d_in, d_out);
+  return launch_tiled<uint4>(ctx, s, p, d_in, d_out);
+}
+
+// ---- small elementwise helpers on the contraction path -------------------------------------
+namespace {
+__global__ void add_to_kernel(double* __restrict__ r, const double* __restrict__ a, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) r[i] += a[i];
+}
+__global__ void scale_kernel(double* __restrict__ x, size_t n, double f) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) x[i] *= f;
+}
+__global__ void __launch_bounds__(256) sqnorm_kernel(const double* const* __restrict__ ptrs,
+                                                     const int64_t* __restrict__ sizes, double* __restrict__ out) {
+  const double* p = ptrs[blockIdx.x];
+  const int64_t n = sizes[blockIdx.x];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) { const double v = p[i]; acc += v * v; }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int sft = 128; sft > 0; sft >>= 1) {
+    if ((int)threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+// splitmix64-based counter RNG: value depends only on (seed, global element offset)
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void fill_uniform_kernel(double* __restrict__ x, size_t n, uint64_t seed, uint64_t offset) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint64_t r = splitmix64(seed * 0xD1342543DE82EF95ull + (offset + i));
+    x[i] = (double)(r >> 11) * (2.0 / 9007199254740992.0) - 1.0;  // [-1, 1)
+  }
+}
+int grid_for(tadev_ctx* ctx, size_t n) {
+  size_t b = (n + 1023) / 1024;
+  size_t maxb = (size_t)ctx->num_sms * 16;
+  if (b > maxb) b = maxb;
+  return b ? (int)b : 1;
+}
+}  // namespace
+
+extern "C" int tadev_add_to_f64(tadev_ctx* ctx, tadev_stream s, size_t n, double* d_result, const double* d_arg) {
+  TADEV_REQUIRE(ctx, "tadev_add_to_f64: null ctx");
+  if (!n) return TADEV_OK;
+  TADEV_REQUIRE(d_result && d_arg, "tadev_add_to_f64: null tile");
+  add_to_kernel<<<grid_for(ctx, n), 256, 0, (cudaStream_t)s>>>(d_result, d_arg, n);
+  ctx->launches++;
+  TADEV_CHECK_CUDA(cudaGetLastError());
+  return TADEV_OK;
+}
+extern "C" int tadev_scale_f64(tadev_ctx* ctx, tadev_stream s, size_t n, double* d_x, double factor) {
+  TADEV_REQUIRE(ctx, "tadev_scale_f64: null ctx");
+  if (!n) return TADEV_OK;
+  TADEV_REQUIRE(d_x, "tadev_scale_f64: null tile");
+  scale_kernel<<<grid_for(ctx, n), 256, 0, (cudaStream_t)s>>>(d_x, n, factor);
+  ctx->launches++;
+  TADEV_CHECK_CUDA(cudaGetLastError());
+  return TADEV_OK;
+}
+extern "C" int tadev_tile_sqnorms_f64(tadev_ctx* ctx, tadev_stream s, int ntiles, const double* const* d_ptrs,
+                                      const int64_t* d_sizes, double* d_out) {
+  TADEV_REQUIRE(ctx, "tadev_tile_sqnorms_f64: null ctx");
+  if (ntiles <= 0) return TADEV_OK;
+  TADEV_REQUIRE(d_ptrs && d_sizes && d_out, "tadev_tile_sqnorms_f64: null arrays");
+  sqnorm_kernel<<<ntiles, 256, 0, (cudaStream_t)s>>>(d_ptrs, d_sizes, d_out);
+  ctx->launches++;
+  TADEV_CHECK_CUDA(cudaGetLastError());
+  return TADEV_OK;
+}
+extern "C" int tadev_fill_uniform_f64(tadev_ctx* ctx, tadev_stream s, double* d_x, size_t n, uint64_t seed,
+                                      uint64_t offset) {
+  TADEV_REQUIRE(ctx, "tadev_fill_uniform_f64: null ctx");
+  if (!n) return TADEV_OK;
+  TADEV_REQUIRE(d_x, "tadev_fill_uniform_f64: null");
+  fill_uniform_kernel<<<grid_for(ctx, n), 256, 0, (cudaStream_t)s>>>(d_x, n, seed, offset);
+  ctx->launches++;
+  TADEV_CHECK_CUDA(cudaGetLastError());
+  return TADEV_OK;
+}
