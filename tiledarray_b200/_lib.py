@@ -114,6 +114,22 @@ PROTOTYPES = {
 _lib = None
 
 
+def _preload_nccl() -> None:
+    """libtadev.so needs libnccl.so.2. PyTorch ships a newer NCCL than the system one and both
+    have the same SONAME, so whichever is mapped first serves the whole process: map the
+    PyTorch-bundled copy first (when present) so that a later ``import torch`` still finds every
+    symbol it was built against."""
+    import sys
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+            except OSError:
+                pass
+
+
 def load() -> C.CDLL:
     """Load libtadev.so; raises if it has not been built (no fallback)."""
     global _lib
@@ -123,7 +139,8 @@ def load() -> C.CDLL:
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(tiledarray_b200 has no CPU or pure-Python compute path)")
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    _preload_nccl()
+    lib = C.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res

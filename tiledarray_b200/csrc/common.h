@@ -57,6 +57,9 @@ struct tadev_ctx {
   ncclComm* row_comm = nullptr;  // ranks sharing my grid row   (A column-panels travel here)
   ncclComm* col_comm = nullptr;  // ranks sharing my grid column (B row-panels travel here)
   int rank = 0, nranks = 1, Pr = 1, Pc = 1, my_r = 0, my_c = 0;
+  // grouped-GEMM launch policy
+  int gemm_sm_reserve = 0;          // SMs left free by the persistent kernel (for NCCL's CTAs)
+  bool force_generic_gemm = false;  // TADEV_GEMM_GENERIC=1: always use the cp.async kernel
 };
 
 // Obtain a staging slot of at least `bytes` for stream s. Returns host + device pointers; the
@@ -67,6 +70,10 @@ int tadev_stage(tadev_ctx* ctx, cudaStream_t s, size_t bytes, void** h, void** d
 int launch_gemm_grouped_f64(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, double alpha,
                             const tadev_gemm_group* d_groups, int ngroups, const tadev_gemm_task* d_tasks,
                             const int32_t* d_tile_prefix, int total_cta_tiles, bool aligned16);
+
+int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, double alpha,
+                               const tadev_gemm_group* d_groups, int ngroups, const tadev_gemm_task* d_tasks,
+                               const int32_t* d_tile_prefix, int total_cta_tiles, int* d_counter, int sm_reserve);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -47,6 +47,7 @@ extern "C" int tadev_init(int device, size_t pool_bytes, tadev_ctx** out) {
   TADEV_CHECK_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thresh));
   int nstreams = 3;  // TA_DEVICE_NUM_STREAMS default (external/device.h:422-441)
   if (const char* e = getenv("TA_DEVICE_NUM_STREAMS")) nstreams = atoi(e) > 0 ? atoi(e) : nstreams;
+  if (const char* e = getenv("TADEV_GEMM_GENERIC")) ctx->force_generic_gemm = atoi(e) != 0;
   int lo = 0, hi = 0;
   TADEV_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   ctx->streams.resize(nstreams);

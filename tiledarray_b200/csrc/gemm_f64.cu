@@ -283,6 +283,13 @@ static bool batch_aligned16(int opA, int opB, const tadev_gemm_group* groups, in
   return true;
 }
 
+// The warp-specialised bulk-copy kernel additionally needs every contracted extent % 4 == 0.
+static bool batch_k_mult4(const tadev_gemm_task* tasks, int ntasks) {
+  for (int ti = 0; ti < ntasks; ++ti)
+    if (tasks[ti].k & 3) return false;
+  return true;
+}
+
 extern "C" int tadev_gemm_grouped_f64(tadev_ctx* ctx, tadev_stream s_, int opA, int opB, double alpha,
                                       const tadev_gemm_group* h_groups, int ngroups,
                                       const tadev_gemm_task* h_tasks, int ntasks) {
@@ -317,18 +324,26 @@ extern "C" int tadev_gemm_grouped_f64(tadev_ctx* ctx, tadev_stream s_, int opA, 
   const size_t pb = sizeof(int32_t) * (size_t)(ngroups + 1);
   const size_t off_t = (gb + 15) & ~size_t(15);
   const size_t off_p = (off_t + tb + 15) & ~size_t(15);
+  const size_t off_c = (off_p + pb + 15) & ~size_t(15);  // tile counter of the persistent kernel
   void *h = nullptr, *d = nullptr;
   cudaEvent_t done;
-  int rc = tadev_stage(ctx, s, off_p + pb, &h, &d, &done);
+  int rc = tadev_stage(ctx, s, off_c + 16, &h, &d, &done);
   if (rc) return rc;
   memcpy(h, h_groups, gb);
   if (tb) memcpy((char*)h + off_t, h_tasks, tb);
   memcpy((char*)h + off_p, prefix.data(), pb);
-  TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, off_p + pb, cudaMemcpyHostToDevice, s));
+  memset((char*)h + off_c, 0, 16);
+  TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, off_c + 16, cudaMemcpyHostToDevice, s));
   const bool al = batch_aligned16(opA, opB, h_groups, ngroups, h_tasks);
-  rc = launch_gemm_grouped_f64(ctx, s, opA, opB, alpha, (const tadev_gemm_group*)d, ngroups,
-                               (const tadev_gemm_task*)((char*)d + off_t),
-                               (const int32_t*)((char*)d + off_p), (int)total, al);
+  const bool ws = al && batch_k_mult4(h_tasks, ntasks) && !ctx->force_generic_gemm;
+  if (ws)
+    rc = launch_gemm_grouped_f64_ws(ctx, s, opA, opB, alpha, (const tadev_gemm_group*)d, ngroups,
+                                    (const tadev_gemm_task*)((char*)d + off_t), (const int32_t*)((char*)d + off_p),
+                                    (int)total, (int*)((char*)d + off_c), ctx->gemm_sm_reserve);
+  else
+    rc = launch_gemm_grouped_f64(ctx, s, opA, opB, alpha, (const tadev_gemm_group*)d, ngroups,
+                                 (const tadev_gemm_task*)((char*)d + off_t),
+                                 (const int32_t*)((char*)d + off_p), (int)total, al);
   TADEV_CHECK_CUDA(cudaEventRecord(done, s));
   return rc;
 }

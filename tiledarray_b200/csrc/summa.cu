@@ -50,6 +50,9 @@ extern "C" int tadev_comm_init(tadev_ctx* ctx, const void* unique_id128, int ran
   memcpy(&id, unique_id128, sizeof(id));
   TADEV_CHECK_NCCL(ncclCommInitRank(&ctx->world, nranks, id, rank));
   ctx->rank = rank; ctx->nranks = nranks; ctx->Pr = Pr; ctx->Pc = Pc;
+  // leave a few SMs to NCCL's broadcast CTAs so panel traffic overlaps the persistent GEMM
+  ctx->gemm_sm_reserve = (Pr * Pc > 1) ? 4 : 0;
+  if (const char* e = getenv("TADEV_SM_RESERVE")) ctx->gemm_sm_reserve = atoi(e);
   const bool in_grid = rank < Pr * Pc;
   ctx->my_r = in_grid ? rank / Pc : -1;  // proc_grid.h: rank_row = rank / proc_cols
   ctx->my_c = in_grid ? rank % Pc : -1;
@@ -64,6 +67,7 @@ extern "C" int tadev_comm_destroy(tadev_ctx* ctx) {
   if (ctx->col_comm) { ncclCommDestroy(ctx->col_comm); ctx->col_comm = nullptr; }
   if (ctx->world) { ncclCommDestroy(ctx->world); ctx->world = nullptr; }
   ctx->rank = 0; ctx->nranks = 1; ctx->Pr = ctx->Pc = 1; ctx->my_r = ctx->my_c = 0;
+  ctx->gemm_sm_reserve = 0;
   return TADEV_OK;
 }
 

@@ -132,8 +132,9 @@ class Device:
         check(self.lib.tadev_gemm_f64(self.ctx, stream or self.stream, opA, opB, m, n, k, alpha, A.ptr, B.ptr, beta,
                                       Cbuf.ptr))
 
-    def gemm_grouped(self, opA: int, opB: int, alpha: float, groups: Sequence[tuple], stream=None) -> None:
-        """groups: sequence of (C_ptr, m, n, accumulate, [(A_ptr, B_ptr, k), ...])."""
+    @staticmethod
+    def make_groups(groups: Sequence[tuple]):
+        """Pack [(C_ptr, m, n, accumulate, [(A_ptr, B_ptr, k), ...]), ...] into C-ABI descriptor arrays."""
         ng = len(groups)
         nt = sum(len(g[4]) for g in groups)
         G = (GemmGroup * max(ng, 1))()
@@ -144,7 +145,15 @@ class Device:
             for (a, b, k) in tl:
                 T[t] = GemmTask(a, b, k, 0)
                 t += 1
+        return G, ng, T, nt
+
+    def gemm_grouped_packed(self, opA: int, opB: int, alpha: float, packed, stream=None) -> None:
+        G, ng, T, nt = packed
         check(self.lib.tadev_gemm_grouped_f64(self.ctx, stream or self.stream, opA, opB, alpha, G, ng, T, nt))
+
+    def gemm_grouped(self, opA: int, opB: int, alpha: float, groups: Sequence[tuple], stream=None) -> None:
+        """groups: sequence of (C_ptr, m, n, accumulate, [(A_ptr, B_ptr, k), ...])."""
+        self.gemm_grouped_packed(opA, opB, alpha, self.make_groups(groups), stream)
 
     # ---- permutation / elementwise ---------------------------------------------------------
     def permute(self, extent: Sequence[int], perm: Sequence[int], elem_bytes: int, src: DeviceBuffer,
