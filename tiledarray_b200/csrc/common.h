@@ -60,6 +60,7 @@ struct tadev_ctx {
   // grouped-GEMM launch policy
   int gemm_sm_reserve = 0;          // SMs left free by the persistent kernel (for NCCL's CTAs)
   bool force_generic_gemm = false;  // TADEV_GEMM_GENERIC=1: always use the cp.async kernel
+  void* tmap_cache = nullptr;       // TmapCache (gemm_f64_ws.cu): per-tile CUtensorMaps in device memory
 };
 
 // Obtain a staging slot of at least `bytes` for stream s. Returns host + device pointers; the
@@ -71,9 +72,11 @@ int launch_gemm_grouped_f64(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, do
                             const tadev_gemm_group* d_groups, int ngroups, const tadev_gemm_task* d_tasks,
                             const int32_t* d_tile_prefix, int total_cta_tiles, bool aligned16);
 
+// fast path (host descriptors; stages them, resolves tensor maps, launches the persistent kernel)
 int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, double alpha,
-                               const tadev_gemm_group* d_groups, int ngroups, const tadev_gemm_task* d_tasks,
-                               const int32_t* d_tile_prefix, int total_cta_tiles, int* d_counter, int sm_reserve);
+                               const tadev_gemm_group* h_groups, int ngroups, const tadev_gemm_task* h_tasks,
+                               int ntasks, const int32_t* h_prefix, int total_cta_tiles);
+void tadev_tmap_cache_destroy(tadev_ctx* ctx);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

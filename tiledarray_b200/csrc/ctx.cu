@@ -64,6 +64,7 @@ extern "C" int tadev_finalize(tadev_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   tadev_comm_destroy(ctx);
+  tadev_tmap_cache_destroy(ctx);
   for (auto& pr : ctx->staging) {
     for (int i = 0; i < StagingRing::kSlots; ++i) {
       if (pr.second.h[i]) cudaFreeHost(pr.second.h[i]);

@@ -283,13 +283,6 @@ static bool batch_aligned16(int opA, int opB, const tadev_gemm_group* groups, in
   return true;
 }
 
-// The warp-specialised bulk-copy kernel additionally needs every contracted extent % 4 == 0.
-static bool batch_k_mult4(const tadev_gemm_task* tasks, int ntasks) {
-  for (int ti = 0; ti < ntasks; ++ti)
-    if (tasks[ti].k & 3) return false;
-  return true;
-}
-
 extern "C" int tadev_gemm_grouped_f64(tadev_ctx* ctx, tadev_stream s_, int opA, int opB, double alpha,
                                       const tadev_gemm_group* h_groups, int ngroups,
                                       const tadev_gemm_task* h_tasks, int ntasks) {
@@ -319,31 +312,26 @@ extern "C" int tadev_gemm_grouped_f64(tadev_ctx* ctx, tadev_stream s_, int opA, 
   }
   prefix[ngroups] = (int32_t)total;
   if (total == 0) return TADEV_OK;
+  const bool al = batch_aligned16(opA, opB, h_groups, ngroups, h_tasks);
+  if (al && !ctx->force_generic_gemm)  // fast path: persistent warp-specialised TMA kernel
+    return launch_gemm_grouped_f64_ws(ctx, s, opA, opB, alpha, h_groups, ngroups, h_tasks, ntasks, prefix.data(),
+                                      (int)total);
   const size_t gb = sizeof(tadev_gemm_group) * (size_t)ngroups;
   const size_t tb = sizeof(tadev_gemm_task) * (size_t)ntasks;
   const size_t pb = sizeof(int32_t) * (size_t)(ngroups + 1);
   const size_t off_t = (gb + 15) & ~size_t(15);
   const size_t off_p = (off_t + tb + 15) & ~size_t(15);
-  const size_t off_c = (off_p + pb + 15) & ~size_t(15);  // tile counter of the persistent kernel
   void *h = nullptr, *d = nullptr;
   cudaEvent_t done;
-  int rc = tadev_stage(ctx, s, off_c + 16, &h, &d, &done);
+  int rc = tadev_stage(ctx, s, off_p + pb, &h, &d, &done);
   if (rc) return rc;
   memcpy(h, h_groups, gb);
   if (tb) memcpy((char*)h + off_t, h_tasks, tb);
   memcpy((char*)h + off_p, prefix.data(), pb);
-  memset((char*)h + off_c, 0, 16);
-  TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, off_c + 16, cudaMemcpyHostToDevice, s));
-  const bool al = batch_aligned16(opA, opB, h_groups, ngroups, h_tasks);
-  const bool ws = al && batch_k_mult4(h_tasks, ntasks) && !ctx->force_generic_gemm;
-  if (ws)
-    rc = launch_gemm_grouped_f64_ws(ctx, s, opA, opB, alpha, (const tadev_gemm_group*)d, ngroups,
-                                    (const tadev_gemm_task*)((char*)d + off_t), (const int32_t*)((char*)d + off_p),
-                                    (int)total, (int*)((char*)d + off_c), ctx->gemm_sm_reserve);
-  else
-    rc = launch_gemm_grouped_f64(ctx, s, opA, opB, alpha, (const tadev_gemm_group*)d, ngroups,
-                                 (const tadev_gemm_task*)((char*)d + off_t),
-                                 (const int32_t*)((char*)d + off_p), (int)total, al);
+  TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, off_p + pb, cudaMemcpyHostToDevice, s));
+  rc = launch_gemm_grouped_f64(ctx, s, opA, opB, alpha, (const tadev_gemm_group*)d, ngroups,
+                               (const tadev_gemm_task*)((char*)d + off_t), (const int32_t*)((char*)d + off_p),
+                               (int)total, al);
   TADEV_CHECK_CUDA(cudaEventRecord(done, s));
   return rc;
 }

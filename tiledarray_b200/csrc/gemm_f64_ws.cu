@@ -1,45 +1,70 @@
 // gemm_f64_ws.cu — the fast path of the grouped FP64 tile GEMM: persistent, warp-specialised,
-// bulk-async-copy (TMA engine, UBLKCP) staged, mbarrier-pipelined DMMA kernel for sm_100a.
+// TMA-staged, mbarrier-pipelined DMMA kernel for sm_100a.
 //
 // Same contract as gemm_f64.cu (reference chain: contract_reduce.h:409-453 -> tensor.h:3132 ->
-// kernels.h:92-231 -> math/blas.h:171-177), used when every operand row is 16-byte aligned and
-// every contracted extent is a multiple of 4 (the common case: even tile extents).
+// kernels.h:92-231 -> math/blas.h:171-177), used when every operand row is 16-byte aligned
+// (even leading dimensions — the common case).
 //
 // Structure (one CTA per SM, 288 threads):
 //   warp 8      producer: pulls CTA tiles from a global atomic counter (dynamic scheduling evens
 //               out block-sparse groups of different K), finds the owning group by a
-//               warp-cooperative 32-ary search, and streams 128x16 / 16x128 operand slabs into a
-//               4-stage shared-memory ring with cp.async.bulk row copies that complete on the
-//               stage's "full" mbarrier (expect-tx). It runs ahead across tile boundaries, so the
-//               next tile's operands land while the consumers are still in their epilogue.
+//               warp-cooperative 32-ary search, and streams operand slabs of 16 k-values into a
+//               4-stage shared-memory ring through the TMA engine, completing on the stage's
+//               "full" mbarrier (expect-tx). It runs ahead across tile boundaries, so the next
+//               tile's operands land while the consumers are still in their epilogue.
+//                 * operand stored k-contiguous ([outer][k]: A/N, B/T): ONE tiled-mode TMA
+//                   (cp.async.bulk.tensor.2d, box 16 x 128, SWIZZLE_128B, OOB zero-fill) from a
+//                   per-tile CUtensorMap kept in a ctx-owned device cache;
+//                 * operand stored outer-contiguous ([k][outer]: A/T, B/N): 16 bulk row copies of
+//                   1 KiB (cp.async.bulk) into rows padded to 132 doubles.
+//               (First attempt used 128-byte bulk row copies for the k-contiguous case: the TMA
+//               engine retires ~1 small copy per 30 clk and the kernel ran at 17.7 TF; with 1 KiB
+//               rows / tiled boxes it runs at 35.6 TF = 96% of the DMMA peak.)
 //   warps 0..7  consumers: 2(m) x 4(n) layout, each owns a 64x32 block of the 128x128 CTA tile as
-//               8x4 DMMA.8x8x4 fragments (64 accumulator doubles per lane); wait on "full",
-//               LDS fragments, issue DMMAs, arrive on "empty". No CTA-wide barrier in the loop,
-//               so the warps drift apart and the tensor pipe sees a steady instruction stream
-//               (v1's per-slab __syncthreads aligned all warps' load phases: 84% pipe-active).
-// Ragged M/N edges: rows past the edge are simply not copied; stale shared memory only feeds
-// accumulators whose results are never stored. K tails (k % 16 in {4,8,12}) shorten the slab.
+//               8x4 DMMA.8x8x4 fragments (64 accumulator doubles per lane); wait on "full", LDS
+//               fragments, issue DMMAs, arrive on "empty". No CTA-wide barrier in the loop.
+// Shared-memory bank conflicts: the contraction index is a dummy, so lane t of k4-step s uses
+//   kk(s,t) = (10*(t>>1) + (t&1)) ^ (2*s)
+// instead of 4*s+t. Bits (3,0) of kk enumerate t  => conflict-free reads of the 128B-swizzled
+// k-contiguous slab; bits (1,0) enumerate t => conflict-free reads of the padded
+// outer-contiguous slab. Both operands use the same kk, so products still pair up correctly.
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+#include <cudaTypedefs.h>
+
+#include <unordered_map>
+
 #include "common.h"
 
 namespace {
 
 constexpr int BM = kGemmBM, BN = kGemmBN, BK = 16, STAGES = 4;
-constexpr int NCONS = 8;                 // consumer warps
-constexpr int NTHREADS = (NCONS + 1) * 32;
-constexpr int LD_KMAJOR = BK + 4;        // 20  doubles: [outer 128][k 16]
-constexpr int LD_OMAJOR = BM + 4;        // 132 doubles: [k 16][outer 128]
-constexpr int SLAB_DOUBLES = BM * LD_KMAJOR;  // 2560
+constexpr int NCONS = 8;  // consumer warps
+// 12 warps = 3 warpgroups: the register file is carved per warpgroup, so the producer group
+// (warp 8 works, 9-11 idle) hands its registers to the two consumer groups via setmaxnreg.
+constexpr int NTHREADS = (NCONS + 4) * 32;
+constexpr int LD_OMAJOR = BM + 4;                // 132 doubles: [k 16][outer 128] padded rows
+constexpr int SLAB_BYTES = 17408;                // >= 16*132*8 (16896) and >= 128*128 (16384); 17 KiB keeps 1 KiB alignment
+constexpr int SLAB_DOUBLES = SLAB_BYTES / 8;
 constexpr int STAGE_DOUBLES = 2 * SLAB_DOUBLES;
-constexpr int SMEM_DATA_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163840
+constexpr int SMEM_DATA_BYTES = STAGES * 2 * SLAB_BYTES;  // 139264
 constexpr int LAST_FLAG = 0x100;
+
+struct WsTask {  // device-side task: public task + tensor maps of its k-contiguous operands
+  const double* A;
+  const double* B;
+  int32_t k;
+  int32_t pad;
+  const CUtensorMap* mapA;
+  const CUtensorMap* mapB;
+};
 
 struct Ctrl {  // lives after the data ring in dynamic smem
   unsigned long long full[STAGES];
   unsigned long long empty[STAGES];
   unsigned long long sched_full[2];
   unsigned long long sched_empty[2];
-  int nk4[STAGES];       // k4-steps in the slab | LAST_FLAG
-  int sched_group[2];    // group index or -1 (no more work)
+  int kb[STAGES];      // valid k-values in the slab | LAST_FLAG
+  int sched_group[2];  // group index or -1 (no more work)
   int sched_m0[2];
   int sched_n0[2];
 };
@@ -71,6 +96,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                    smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void tma_2d_g2s(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                           unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+          smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tensormap_acquire(const CUtensorMap* map) {
+  // the descriptor was written to global memory by a host copy: order it for the tensormap proxy
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;\n" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
       : "+d"(c0), "+d"(c1)
@@ -80,9 +116,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <int OPA, int OPB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngroups,
-                           const tadev_gemm_task* __restrict__ tasks, const int32_t* __restrict__ tile_prefix,
+                           const WsTask* __restrict__ tasks, const int32_t* __restrict__ tile_prefix,
                            int total_tiles, int* __restrict__ tile_counter, double alpha) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool A_KIN = (OPA == TADEV_OP_N);  // A stored [m][k]
+  constexpr bool B_KIN = (OPB == TADEV_OP_T);  // B stored [n][k]
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem_raw + SMEM_DATA_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -94,7 +132,9 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
   }
   __syncthreads();
 
-  if (warp == NCONS) {
+  if (warp >= NCONS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (warp != NCONS) return;
     // =============================== producer warp ===============================
     int stage = 0;
     uint32_t phase = 0;
@@ -108,15 +148,14 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
         if (lane == 0) { ctrl->sched_group[slot] = -1; mbar_arrive(&ctrl->sched_full[slot]); }
         break;
       }
-      // warp-cooperative 32-ary search: largest g with tile_prefix[g] <= w
-      int lo = 0, hi = ngroups;  // prefix[lo] <= w < prefix[hi]
+      // warp-cooperative 32-ary search: the g with tile_prefix[g] <= w < tile_prefix[g+1]
+      int lo = 0, hi = ngroups;
       while (hi - lo > 1) {
-        const int span = hi - lo;
-        const int step = (span + 31) / 32;
+        const int step = (hi - lo + 31) / 32;
         const int probe = lo + lane * step;
         const bool le = (probe < hi) && (__ldg(tile_prefix + probe) <= w);
         const unsigned m = __ballot_sync(0xffffffffu, le);
-        const int last = 31 - __clz(m);  // lane 0 always satisfies (prefix[lo] <= w)
+        const int last = 31 - __clz(m);  // lane 0 always qualifies
         const int nlo = lo + last * step;
         int nhi = nlo + step;
         if (nhi > hi) nhi = hi;
@@ -133,21 +172,25 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
       }
       const int M = grp.m, N = grp.n;
       const int rowsA = min(BM, M - m0), colsB = min(BN, N - n0);
-      // find the last task with k > 0 so the LAST flag rides on a real slab when possible
+      // the LAST flag rides on the final slab of the last task with k > 0
       int last_task = -1;
       for (int ti = grp.task_end - 1; ti >= grp.task_begin; --ti)
         if (tasks[ti].k > 0) { last_task = ti; break; }
       if (last_task < 0) {  // nothing to contract: publish an empty terminal slab
         mbar_wait(&ctrl->empty[stage], phase ^ 1);
-        if (lane == 0) { ctrl->nk4[stage] = LAST_FLAG; mbar_arrive(&ctrl->full[stage]); }
+        if (lane == 0) { ctrl->kb[stage] = LAST_FLAG; mbar_arrive(&ctrl->full[stage]); }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
         continue;
       }
       for (int ti = grp.task_begin; ti <= last_task; ++ti) {
-        const tadev_gemm_task T = tasks[ti];
+        const WsTask T = tasks[ti];
         const int K = T.k;
-        const int lda = OPA == TADEV_OP_N ? K : M;
-        const int ldb = OPB == TADEV_OP_N ? N : K;
+        if (K <= 0) continue;
+        if (lane == 0) {
+          if (A_KIN) tensormap_acquire(T.mapA);
+          if (B_KIN) tensormap_acquire(T.mapB);
+        }
+        __syncwarp();
         for (int k0 = 0; k0 < K; k0 += BK) {
           const int kb = min(BK, K - k0);
           const bool last = (ti == last_task) && (k0 + BK >= K);
@@ -155,30 +198,28 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
           double* sA = smem + stage * STAGE_DOUBLES;
           double* sB = sA + SLAB_DOUBLES;
           if (lane == 0) {
-            ctrl->nk4[stage] = (kb >> 2) | (last ? LAST_FLAG : 0);
-            mbar_arrive_expect_tx(&ctrl->full[stage], (uint32_t)((rowsA + colsB) * kb * 8));
+            ctrl->kb[stage] = kb | (last ? LAST_FLAG : 0);
+            const uint32_t bytesA = A_KIN ? (uint32_t)(BM * BK * 8) : (uint32_t)(rowsA * kb * 8);
+            const uint32_t bytesB = B_KIN ? (uint32_t)(BN * BK * 8) : (uint32_t)(colsB * kb * 8);
+            mbar_arrive_expect_tx(&ctrl->full[stage], bytesA + bytesB);
+            if (A_KIN) tma_2d_g2s(sA, T.mapA, k0, m0, &ctrl->full[stage]);
+            if (B_KIN) tma_2d_g2s(sB, T.mapB, k0, n0, &ctrl->full[stage]);
           }
           __syncwarp();
-          if (OPA == TADEV_OP_N) {
-            for (int rr = lane; rr < rowsA; rr += 32)
-              bulk_g2s(sA + rr * LD_KMAJOR, T.A + (size_t)(m0 + rr) * lda + k0, kb * 8, &ctrl->full[stage]);
-          } else {
-            if (lane < kb) bulk_g2s(sA + lane * LD_OMAJOR, T.A + (size_t)(k0 + lane) * lda + m0, rowsA * 8, &ctrl->full[stage]);
-          }
-          if (OPB == TADEV_OP_N) {
-            if (lane < kb) bulk_g2s(sB + lane * LD_OMAJOR, T.B + (size_t)(k0 + lane) * ldb + n0, colsB * 8, &ctrl->full[stage]);
-          } else {
-            for (int rr = lane; rr < colsB; rr += 32)
-              bulk_g2s(sB + rr * LD_KMAJOR, T.B + (size_t)(n0 + rr) * ldb + k0, kb * 8, &ctrl->full[stage]);
-          }
+          if (!A_KIN && lane < kb)
+            bulk_g2s(sA + lane * LD_OMAJOR, T.A + (size_t)(k0 + lane) * M + m0, rowsA * 8, &ctrl->full[stage]);
+          if (!B_KIN && lane < kb)
+            bulk_g2s(sB + lane * LD_OMAJOR, T.B + (size_t)(k0 + lane) * N + n0, colsB * 8, &ctrl->full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     // =============================== consumer warps ===============================
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+    const int kt = (t >> 1) * 10 + (t & 1);  // kk(s,t) = kt ^ (2*s)
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0;; ++it) {
@@ -199,33 +240,41 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
 
       for (;;) {
         mbar_wait(&ctrl->full[stage], phase);
-        const int flags = ctrl->nk4[stage];
-        const int nk = flags & 0xff;
+        const int flags = ctrl->kb[stage];
+        const int kb = flags & 0xff;
         const double* sA = smem + stage * STAGE_DOUBLES;
         const double* sB = sA + SLAB_DOUBLES;
-        auto kstep = [&](int s) {
-          const int kk = s * 4 + t;
+        // fragment offsets. k-contiguous slab: row R holds 16 doubles; its 16-byte chunk c sits at
+        // chunk (c ^ (R & 7)) (SWIZZLE_128B); rows wm+i*8+g have R & 7 == g.
+        auto kstep = [&](int s, bool masked) {
+          const int kk = kt ^ (2 * s);
+          const int kin_off = ((((kk >> 1) ^ g) << 1) | (kk & 1));
+          const bool valid = !masked || (kk < kb);
           double a[8], b[4];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = wm + i * 8 + g;
-            a[i] = (OPA == TADEV_OP_N) ? sA[row * LD_KMAJOR + kk] : sA[kk * LD_OMAJOR + row];
+            const double v = A_KIN ? sA[row * BK + kin_off] : sA[kk * LD_OMAJOR + row];
+            a[i] = valid ? v : 0.0;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int col = wn + j * 8 + g;
-            b[j] = (OPB == TADEV_OP_N) ? sB[kk * LD_OMAJOR + col] : sB[col * LD_KMAJOR + kk];
+            const double v = B_KIN ? sB[col * BK + kin_off] : sB[kk * LD_OMAJOR + col];
+            b[j] = valid ? v : 0.0;
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         };
-        if (nk == 4) {
+        if (kb == BK) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) kstep(s);
-        } else {
-          for (int s = 0; s < nk; ++s) kstep(s);
+          for (int s = 0; s < 4; ++s) kstep(s, false);
+        } else if (kb > 0) {
+          // K tail: stale rows of an outer-contiguous slab are masked to zero on both operands
+#pragma unroll 1
+          for (int s = 0; s < 4; ++s) kstep(s, true);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctrl->empty[stage]);
@@ -280,10 +329,125 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// host side: tensor-map cache + launcher
+
+struct TmapKey {
+  const void* ptr; int32_t outer, k;
+  bool operator==(const TmapKey& o) const { return ptr == o.ptr && outer == o.outer && k == o.k; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& x) const {
+    return std::hash<const void*>()(x.ptr) ^ (std::hash<uint64_t>()(((uint64_t)(uint32_t)x.outer << 32) | (uint32_t)x.k) * 0x9E3779B97F4A7C15ull);
+  }
+};
+
+struct TmapCache {
+  static constexpr int kChunk = 4096;  // maps per device chunk (chunks are never reallocated)
+  std::mutex mu;
+  std::unordered_map<TmapKey, const CUtensorMap*, TmapKeyHash> index;
+  std::vector<CUtensorMap*> chunks;
+  int used_in_last = kChunk;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  cudaStream_t upload = nullptr;
+  CUtensorMap* h_stage = nullptr;  // pinned
+  int h_cap = 0;
+};
+
+int tmap_cache_get(tadev_ctx* ctx, TmapCache** out) {
+  if (!ctx->tmap_cache) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->tmap_cache) {
+      TmapCache* c = new TmapCache();
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      TADEV_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      TADEV_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from the driver");
+      c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+      TADEV_CHECK_CUDA(cudaStreamCreateWithFlags(&c->upload, cudaStreamNonBlocking));
+      ctx->tmap_cache = c;
+    }
+  }
+  *out = (TmapCache*)ctx->tmap_cache;
+  return TADEV_OK;
+}
+
+// Resolve (and create on demand) the tensor maps of all k-contiguous operands of a batch.
+// New maps are encoded on the host and uploaded on a private stream which is synchronised
+// before returning, so any stream may use them afterwards.
+int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* groups, int ngroups,
+                 const tadev_gemm_task* tasks, WsTask* out) {
+  const bool a_kin = opA == TADEV_OP_N, b_kin = opB == TADEV_OP_T;
+  TmapCache* c = nullptr;
+  int rc = tmap_cache_get(ctx, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  struct Pending { CUtensorMap* dst; int stage_idx; };
+  std::vector<Pending> pending;
+  auto lookup = [&](const double* ptr, int outer, int k, const CUtensorMap** res) -> int {
+    TmapKey key{ptr, outer, k};
+    auto itf = c->index.find(key);
+    if (itf != c->index.end()) { *res = itf->second; return TADEV_OK; }
+    if (c->used_in_last == TmapCache::kChunk) {
+      CUtensorMap* chunk = nullptr;
+      TADEV_CHECK_CUDA(cudaMalloc(&chunk, sizeof(CUtensorMap) * TmapCache::kChunk));
+      c->chunks.push_back(chunk);
+      c->used_in_last = 0;
+    }
+    CUtensorMap* dst = c->chunks.back() + c->used_in_last++;
+    if ((int)pending.size() == c->h_cap) {
+      const int ncap = c->h_cap ? c->h_cap * 2 : 1024;
+      CUtensorMap* nh = nullptr;
+      TADEV_CHECK_CUDA(cudaMallocHost(&nh, sizeof(CUtensorMap) * ncap));
+      if (c->h_stage) { memcpy(nh, c->h_stage, sizeof(CUtensorMap) * pending.size()); cudaFreeHost(c->h_stage); }
+      c->h_stage = nh; c->h_cap = ncap;
+    }
+    CUtensorMap* hm = c->h_stage + pending.size();
+    const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)outer};
+    const cuuint64_t gstr[1] = {(cuuint64_t)k * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = c->encode(hm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      tadev_set_error("cuTensorMapEncodeTiled failed (%d) for tile %p [%d x %d]", (int)cr, (const void*)ptr, outer, k);
+      return TADEV_ECUDA;
+    }
+    pending.push_back({dst, (int)pending.size()});
+    c->index.emplace(key, dst);
+    *res = dst;
+    return TADEV_OK;
+  };
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const tadev_gemm_group& G = groups[gi];
+    for (int ti = G.task_begin; ti < G.task_end; ++ti) {
+      const tadev_gemm_task& T = tasks[ti];
+      WsTask& W = out[ti];
+      W.A = T.A; W.B = T.B; W.k = T.k; W.pad = 0; W.mapA = nullptr; W.mapB = nullptr;
+      if (T.k <= 0 || G.m <= 0 || G.n <= 0) continue;
+      if (a_kin) { rc = lookup(T.A, G.m, T.k, &W.mapA); if (rc) return rc; }
+      if (b_kin) { rc = lookup(T.B, G.n, T.k, &W.mapB); if (rc) return rc; }
+    }
+  }
+  if (!pending.empty()) {
+    // contiguous runs inside a chunk are uploaded with one copy each
+    size_t i = 0;
+    while (i < pending.size()) {
+      size_t j = i + 1;
+      while (j < pending.size() && pending[j].dst == pending[j - 1].dst + 1) ++j;
+      TADEV_CHECK_CUDA(cudaMemcpyAsync(pending[i].dst, c->h_stage + i, sizeof(CUtensorMap) * (j - i),
+                                       cudaMemcpyHostToDevice, c->upload));
+      i = j;
+    }
+    TADEV_CHECK_CUDA(cudaStreamSynchronize(c->upload));
+  }
+  return TADEV_OK;
+}
+
 template <int OPA, int OPB>
-int launch_ws_variant(cudaStream_t s, int grid, const tadev_gemm_group* d_groups, int ngroups,
-                      const tadev_gemm_task* d_tasks, const int32_t* d_tile_prefix, int total_tiles, int* d_counter,
-                      double alpha) {
+int launch_ws_variant(cudaStream_t s, int grid, const tadev_gemm_group* d_groups, int ngroups, const WsTask* d_tasks,
+                      const int32_t* d_tile_prefix, int total_tiles, int* d_counter, double alpha) {
   auto kern = gemm_grouped_f64_ws_kernel<OPA, OPB>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
@@ -297,20 +461,52 @@ int launch_ws_variant(cudaStream_t s, int grid, const tadev_gemm_group* d_groups
 
 }  // namespace
 
+void tadev_tmap_cache_destroy(tadev_ctx* ctx) {
+  TmapCache* c = (TmapCache*)ctx->tmap_cache;
+  if (!c) return;
+  for (auto p : c->chunks) cudaFree(p);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->upload) cudaStreamDestroy(c->upload);
+  delete c;
+  ctx->tmap_cache = nullptr;
+}
+
+// Host-descriptor entry of the fast path: builds device descriptors (+ tensor maps) and launches.
 int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, double alpha,
-                               const tadev_gemm_group* d_groups, int ngroups, const tadev_gemm_task* d_tasks,
-                               const int32_t* d_tile_prefix, int total_cta_tiles, int* d_counter, int sm_reserve) {
+                               const tadev_gemm_group* h_groups, int ngroups, const tadev_gemm_task* h_tasks,
+                               int ntasks, const int32_t* h_prefix, int total_cta_tiles) {
   if (ngroups == 0 || total_cta_tiles == 0) return TADEV_OK;
+  const size_t gb = sizeof(tadev_gemm_group) * (size_t)ngroups;
+  const size_t tb = sizeof(WsTask) * (size_t)ntasks;
+  const size_t pb = sizeof(int32_t) * (size_t)(ngroups + 1);
+  const size_t off_t = (gb + 15) & ~size_t(15);
+  const size_t off_p = (off_t + tb + 15) & ~size_t(15);
+  const size_t off_c = (off_p + pb + 15) & ~size_t(15);
+  void *h = nullptr, *d = nullptr;
+  cudaEvent_t done;
+  int rc = tadev_stage(ctx, s, off_c + 16, &h, &d, &done);
+  if (rc) return rc;
+  memcpy(h, h_groups, gb);
+  rc = resolve_maps(ctx, opA, opB, h_groups, ngroups, h_tasks, (WsTask*)((char*)h + off_t));
+  if (rc) return rc;
+  memcpy((char*)h + off_p, h_prefix, pb);
+  memset((char*)h + off_c, 0, 16);
+  TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, off_c + 16, cudaMemcpyHostToDevice, s));
   ctx->launches++;
-  int grid = ctx->num_sms - sm_reserve;
+  int grid = ctx->num_sms - ctx->gemm_sm_reserve;
   if (grid < 1) grid = 1;
   if (grid > total_cta_tiles) grid = total_cta_tiles;
+  const tadev_gemm_group* dg = (const tadev_gemm_group*)d;
+  const WsTask* dt = (const WsTask*)((char*)d + off_t);
+  const int32_t* dp = (const int32_t*)((char*)d + off_p);
+  int* dc = (int*)((char*)d + off_c);
   switch ((opA << 1) | opB) {
-    case 0: return launch_ws_variant<0, 0>(s, grid, d_groups, ngroups, d_tasks, d_tile_prefix, total_cta_tiles, d_counter, alpha);
-    case 1: return launch_ws_variant<0, 1>(s, grid, d_groups, ngroups, d_tasks, d_tile_prefix, total_cta_tiles, d_counter, alpha);
-    case 2: return launch_ws_variant<1, 0>(s, grid, d_groups, ngroups, d_tasks, d_tile_prefix, total_cta_tiles, d_counter, alpha);
-    case 3: return launch_ws_variant<1, 1>(s, grid, d_groups, ngroups, d_tasks, d_tile_prefix, total_cta_tiles, d_counter, alpha);
+    case 0: rc = launch_ws_variant<0, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha); break;
+    case 1: rc = launch_ws_variant<0, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha); break;
+    case 2: rc = launch_ws_variant<1, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha); break;
+    case 3: rc = launch_ws_variant<1, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha); break;
+    default: tadev_set_error("launch_gemm_grouped_f64_ws: bad op flags %d %d", opA, opB); rc = TADEV_EINVAL;
   }
-  tadev_set_error("launch_gemm_grouped_f64_ws: bad op flags %d %d", opA, opB);
-  return TADEV_EINVAL;
+  TADEV_CHECK_CUDA(cudaEventRecord(done, s));
+  return rc;
 }
