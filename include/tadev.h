@@ -240,6 +240,16 @@ int tadev_summa_schedule(int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt, c
                          int32_t* step_k, int32_t* step_pair_begin, int32_t* nsteps_out,
                          int32_t* pair_i, int32_t* pair_j, int64_t pair_capacity, int64_t* npairs_out);
 
+/* [host] the communication side of the same schedule: every step in which this rank takes part
+ * in a broadcast or contracts. flags: bit0 contract, bit1 A panel broadcast along my grid row
+ * (root column k % Pc), bit2 B panel broadcast along my grid column (root row k % Pr).
+ * a_rows / b_cols are the concatenated panel contents (global tile rows of A(:,k) with i%Pr==r,
+ * global tile cols of B(k,:) with j%Pc==c, non-zero only); *_begin have nsteps+1 entries. */
+int tadev_summa_steps(int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt, const float* a_norms,
+                      const float* b_norms, const float* c_norms, float threshold, int32_t* step_k,
+                      int32_t* step_flags, int32_t* a_begin, int32_t* a_rows, int32_t* b_begin,
+                      int32_t* b_cols, int32_t* nsteps_out);
+
 /* ---- measurement helpers -------------------------------------------------------------------
  * Register-resident DMMA / DFMA issue-rate probes: the FP64 roofline denominator is not in
  * MEASURED_PEAKS.json and must be measured on the box. Returns TFLOP/s. */

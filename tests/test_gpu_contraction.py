@@ -1,0 +1,185 @@
+"""End-to-end contraction through the TiledArray-mirroring API (DistArray / expressions ->
+ContEngine -> tadev_plan_contraction / tadev_shape_* / tadev_permute / tadev_summa_f64) against
+the CPU oracle. These read like tests/expressions_impl.h:1808-2675 (cont, cont_permute,
+scale_cont, cont_non_uniform, outer_product) and tests/dist_eval_contraction_eval.cpp:293-472.
+"""
+import numpy as np
+import pytest
+
+from oracle import ta_oracle as O
+from tests import known_answers as KA
+from tiledarray_b200.tiledarray import ContEngine, DistArray, SparseShape, TiledRange, TiledRange1, TiledArrayException
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _tr(*dims):
+    return TiledRange([TiledRange1(*d) if not isinstance(d, TiledRange1) else d for d in dims])
+
+
+def _uniform(extent, tile):
+    return TiledRange1.make_uniform(extent, tile)
+
+
+def _dense_array(world, tr, rng, integer=False):
+    full = KA.int_tile(rng, tr.elements_shape) if integer else rng.uniform(-1, 1, tr.elements_shape)
+    return DistArray(world, tr).init_from_numpy(full), full
+
+
+def _check(world, target, lidx, ridx, trL, trR, trC, factor=1.0, integer=True, seed=0):
+    rng = np.random.default_rng(seed)
+    a, A = _dense_array(world, trL, rng, integer)
+    b, B = _dense_array(world, trR, rng, integer)
+    c = DistArray(world, trC)
+    expr = a[lidx] * b[ridx]
+    c[target] = expr if factor == 1.0 else factor * expr
+    ref = factor * np.einsum(f"{lidx.replace(',', '')},{ridx.replace(',', '')}->{target.replace(',', '')}", A, B)
+    got = c.to_numpy()
+    if integer:
+        assert np.array_equal(got, ref)
+    else:
+        assert O.rel_frobenius(got, ref) < TOL
+    for x in (a, b, c):
+        x.release()
+    return ContEngine.last_stats
+
+
+def test_cont_dense_matrix(world):
+    """c("m,n") = a("m,k") * b("k,n") — examples/gemm/ta_dense.cpp:174; config 1 in miniature."""
+    t = _uniform(96, 32)
+    st = _check(world, "m,n", "m,k", "k,n", _tr(t, t), _tr(t, t), _tr(t, t))
+    assert st.npairs == 27 and st.nlaunches == 1
+    assert st.flops == 2.0 * 96 ** 3
+
+
+def test_cont_fixture_prime_tiles(world):
+    """Prime tile widths (tests/range_fixture.h:67-132): ragged, odd extents -> generic kernel."""
+    d = TiledRange1(*KA.FIXTURE_BOUNDS)
+    _check(world, "m,n", "m,k", "k,n", _tr(d, d), _tr(d, d), _tr(d, d))
+    _check(world, "m,n", "m,k", "k,n", _tr(d, d), _tr(d, d), _tr(d, d), integer=False, factor=-1.5)
+
+
+@pytest.mark.parametrize("target,lidx,ridx", [
+    ("m,n", "k,m", "k,n"), ("m,n", "m,k", "n,k"), ("m,n", "k,m", "n,k"),  # BLAS-transpose forms (implicit permute)
+    ("n,m", "m,k", "k,n"),                                                # cont_permute: result permutation
+])
+def test_cont_transposes_and_result_permute(world, target, lidx, ridx):
+    dm, dk, dn = TiledRange1(0, 4, 10, 16), TiledRange1(0, 6, 8), TiledRange1(0, 2, 12, 20, 24)
+    dims = {"m": dm, "k": dk, "n": dn}
+    trL = _tr(*[dims[x] for x in lidx.split(",")])
+    trR = _tr(*[dims[x] for x in ridx.split(",")])
+    trC = _tr(*[dims[x] for x in target.split(",")])
+    _check(world, target, lidx, ridx, trL, trR, trC)
+
+
+def test_cont_ccsd_ppl_shape(world):
+    """Config 4 in miniature: R("a,b,i,j") = T("c,d,i,j") * V("a,b,c,d") (examples/gemm/
+    ta_cc_abcd.cpp:240) — both operands matrix_transpose, result permute; ragged
+    occupied/virtual tilings like o=100/64, v=800/64."""
+    o, v = TiledRange1(0, 6, 10), TiledRange1(0, 8, 16, 20)
+    st = _check(world, "a,b,i,j", "c,d,i,j", "a,b,c,d", _tr(v, v, o, o), _tr(v, v, v, v), _tr(v, v, o, o))
+    assert st.permute_ms > 0.0  # the result permutation ran
+    _check(world, "a,b,i,j", "c,d,i,j", "a,b,c,d", _tr(v, v, o, o), _tr(v, v, v, v), _tr(v, v, o, o), integer=False, factor=0.5)
+
+
+def test_cont_general_permutes(world):
+    """Config 5 in miniature: C("i,a,j,b") = A("i,k,a,c") * B("j,c,k,b") — both operands need
+    explicit tile permutations (permtype general), result needs none."""
+    s, b = TiledRange1(0, 2, 6), TiledRange1(0, 4, 8, 10)
+    _check(world, "i,a,j,b", "i,k,a,c", "j,c,k,b", _tr(s, s, b, b), _tr(s, b, s, b), _tr(s, b, s, b))
+    _check(world, "i,a,j,b", "i,k,a,c", "j,c,k,b", _tr(s, s, b, b), _tr(s, b, s, b), _tr(s, b, s, b), integer=False)
+
+
+def test_cont_rank3_and_outer_product(world):
+    d3, d2 = TiledRange1(0, 3, 5), TiledRange1(0, 2, 6, 7)
+    _check(world, "a,b,c", "a,x,y", "y,x,b,c", _tr(d3, d2, d3), _tr(d3, d2, d2, d3), _tr(d3, d2, d3))
+    _check(world, "a,b", "a", "b", _tr(d3), _tr(d2), _tr(d3, d2))  # outer product (k rank 0)
+    _check(world, "i", "i,k", "k", _tr(d2, d3), _tr(d3), _tr(d2))  # matrix-vector
+
+
+def _sparse_pair(world, trL, trR, density, rng, integer=True):
+    def make(tr):
+        full = KA.int_tile(rng, tr.elements_shape) if integer else rng.uniform(-1, 1, tr.elements_shape)
+        norms = np.zeros(tr.tiles_shape, dtype=np.float32)
+        for o in range(tr.ntiles):
+            idx = tr.tile_index(o)
+            if rng.random() < density:
+                blk = full[tr.tile_slices(idx)]
+                norms[idx] = np.float32(np.linalg.norm(blk))  # true Frobenius norm of the tile
+            else:
+                full[tr.tile_slices(idx)] = 0.0
+        sh = SparseShape(world, norms, tr)
+        return DistArray(world, tr, sh).init_from_numpy(full), full, norms
+    return make(trL), make(trR)
+
+
+@pytest.mark.parametrize("density", [0.6, 0.2])
+def test_cont_sparse(world, density):
+    """tests/dist_eval_contraction_eval.cpp:375-472 sparse_eval: block-sparse operands with true
+    tile norms; result shape by device screening == oracle's, bit for bit; values exact; zero
+    result tiles are absent and the dense reference block is all-zero (:434-445)."""
+    rng = np.random.default_rng(int(density * 10))
+    dm, dk, dn = _uniform(40, 8), _uniform(48, 8), _uniform(56, 8)
+    trL, trR = _tr(dm, dk), _tr(dk, dn)
+    (a, A, nA), (b, B, nB) = _sparse_pair(world, trL, trR, density, rng)
+    c = DistArray(world, _tr(dm, dn))
+    c["m,n"] = a["m,k"] * b["k,n"]
+    # shapes: product vs oracle (bit-exact)
+    oa = O.SparseShape.from_tile_norms(nA, O.TiledRange((O.TiledRange1(dm.bounds), O.TiledRange1(dk.bounds))))
+    ob = O.SparseShape.from_tile_norms(nB, O.TiledRange((O.TiledRange1(dk.bounds), O.TiledRange1(dn.bounds))))
+    assert np.array_equal(a.shape.norms.view(np.uint32), oa.norms.view(np.uint32))
+    oc = oa.gemm(ob, 1.0, O.GemmHelper(0, 0, 2, 2, 2))
+    assert np.array_equal(c.shape.norms.view(np.uint32), oc.norms.view(np.uint32))
+    assert c.shape.zero_tile_count == oc.zero_tile_count
+    ref = A @ B
+    assert np.array_equal(c.to_numpy(), ref)
+    for o in range(c.trange.ntiles):
+        if c.is_zero(o):
+            assert o not in c.tiles and not ref[c.trange.tile_slices(c.trange.tile_index(o))].any()
+    st = ContEngine.last_stats
+    want_pairs = int(((oa.norms >= np.float32(oa.threshold)).astype(int) @ (ob.norms >= np.float32(ob.threshold)).astype(int)).sum())
+    assert st.npairs == want_pairs
+    for x in (a, b, c):
+        x.release()
+
+
+def test_cont_sparse_permuted_4index(world):
+    """Sparse + general permutes + result permute: shapes are permuted with the tiles
+    (SparseShape::perm, sparse_shape.h:1222) and the tile list still matches the data."""
+    rng = np.random.default_rng(31)
+    s, b = TiledRange1(0, 2, 6), TiledRange1(0, 4, 8, 10)
+    trL, trR = _tr(s, s, b, b), _tr(s, b, s, b)
+    (a, A, _), (bb, B, _) = _sparse_pair(world, trL, trR, 0.5, rng, integer=False)
+    c = DistArray(world, _tr(b, s, b, s))
+    c["a,i,b,j"] = 2.0 * (a["i,k,a,c"] * bb["j,c,k,b"])
+    ref = 2.0 * np.einsum("ikac,jckb->aibj", A, B)
+    assert O.rel_frobenius(c.to_numpy(), ref) < TOL
+    for x in (a, bb, c):
+        x.release()
+
+
+def test_cont_reference_style_dense_fill(world):
+    """examples/device/ta_dense_device.cpp verification: a.fill(va), b.fill(vb) => every element of
+    c equals Nk*va*vb; config-1 tiling (tile 256) at N=1024."""
+    t = _uniform(1024, 256)
+    a = DistArray(world, _tr(t, t)).fill(1.0)
+    b = DistArray(world, _tr(t, t)).fill(0.5)
+    c = DistArray(world, _tr(t, t))
+    c["m,n"] = a["m,k"] * b["k,n"]
+    assert np.array_equal(c.to_numpy(), np.full((1024, 1024), 512.0))
+    for x in (a, b, c):
+        x.release()
+
+
+def test_cont_errors(world):
+    t, u = _uniform(8, 4), _uniform(8, 2)
+    a = DistArray(world, _tr(t, t)).fill(1.0)
+    b = DistArray(world, _tr(u, t)).fill(1.0)
+    c = DistArray(world, _tr(t, t))
+    with pytest.raises(TiledArrayException):  # inner tilings not congruent (TA_ASSERT in kernels.h:117-131)
+        c["m,n"] = a["m,k"] * b["k,n"]
+    with pytest.raises(TiledArrayException):
+        c["m,n"] = a["m,k,z"] * b["k,n"]
+    for x in (a, b, c):
+        x.release()

@@ -1,0 +1,160 @@
+"""Host-side planning logic of libtadev (no GPU needed) against the oracle, bit for bit."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import ta_oracle as O
+from tiledarray_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    """The C-ABI library loads without a GPU and exports every entry include/tadev.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "tadev.h")).read()
+    declared = set(re.findall(r"\b(tadev_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"tadev_ctx", "tadev_stream"}
+    assert len(declared) >= 40
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, missing
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert b"sm_100a" in lib.tadev_version()
+
+
+def test_no_cpu_fallback_without_device(lib):
+    """On a box without a GPU a context cannot be created: the product has no CPU path."""
+    n = C.c_int()
+    _lib.check(lib.tadev_device_count(C.byref(n)))
+    if n.value > 0:
+        pytest.skip("a CUDA device is present")
+    ctx = C.c_void_p()
+    rc = lib.tadev_init(0, 0, C.byref(ctx))
+    assert rc == _lib.ENODEVICE
+    assert b"no CPU path" in lib.tadev_last_error()
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tiledarray_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def _grid(lib, rank, nprocs, rows, cols, rs, cs):
+    g = _lib.ProcGridC()
+    _lib.check(lib.tadev_proc_grid_make(rank, nprocs, rows, cols, rs, cs, C.byref(g)))
+    return g
+
+
+def test_proc_grid_matches_oracle(lib):
+    """proc_grid.h:97-260 restated twice (C++ product, Python oracle): identical on random cases
+    in the style of tests/proc_grid.cpp:42-155, for every rank of small grids."""
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        nprocs = int(rng.integers(1, 4096)) if trial % 3 else int(rng.integers(1, 17))
+        rows, cols = int(rng.integers(1, 1024)), int(rng.integers(1, 1024))
+        rs, cs = rows * int(rng.integers(1, 512)), cols * int(rng.integers(1, 513))
+        ranks = range(nprocs) if nprocs <= 16 else (0, nprocs // 2, nprocs - 1)
+        for rank in ranks:
+            g, o = _grid(lib, rank, nprocs, rows, cols, rs, cs), O.proc_grid(rank, nprocs, rows, cols, rs, cs)
+            assert (g.proc_rows, g.proc_cols, g.proc_size, g.rank_row, g.rank_col, g.local_rows, g.local_cols,
+                    g.local_size) == (o.proc_rows, o.proc_cols, o.proc_size, o.rank_row, o.rank_col, o.local_rows,
+                                      o.local_cols, o.local_size)
+
+
+def test_cyclic_owner_matches_oracle(lib):
+    own = C.c_int()
+    for rows, cols, pr, pc in ((5, 7, 2, 3), (32, 32, 4, 2), (128, 128, 2, 2), (4, 169, 1, 8)):
+        for t in range(rows * cols):
+            _lib.check(lib.tadev_cyclic_owner(t, cols, pr, pc, C.byref(own)))
+            assert own.value == O.cyclic_owner(t, cols, pr, pc)
+
+
+CONTRACTIONS = [
+    ("m,n", "m,k", "k,n"), ("n,m", "m,k", "k,n"), ("m,n", "k,m", "k,n"), ("m,n", "m,k", "n,k"), ("m,n", "k,m", "n,k"),
+    ("a,b,i,j", "c,d,i,j", "a,b,c,d"), ("i,a,j,b", "i,k,a,c", "j,c,k,b"), ("i,j,a,b", "i,j,c,d", "a,b,c,d"),
+    ("a,b,c", "a,x,y", "y,x,b,c"), ("a,c,b", "a,x,y", "x,y,b,c"), ("i,j", "i,a,b", "b,a,j"), ("i,j", "a,i,b", "j,b,a"),
+    ("a,b", "a", "b"), ("a,b,c,d", "a,b", "c,d"), ("i", "i,k", "k"), ("b,a", "a,k,l", "l,b,k"),
+    ("x,y,z", "x,k", "y,k,z"), ("p,q", "k1,p,k2", "k2,q,k1"),
+]
+
+
+@pytest.mark.parametrize("target,left,right", CONTRACTIONS)
+def test_plan_contraction_matches_oracle(lib, target, left, right):
+    """GEMMPermutationOptimizer (permopt.h:254-376) + result permutation, C++ vs oracle."""
+    p = _lib.ContractionPlanC()
+    _lib.check(lib.tadev_plan_contraction(target.encode(), left.encode(), right.encode(), C.byref(p)))
+    o = O.plan_contraction(target, left, right)
+
+    def perm(arr, rank):
+        return None if arr[0] < 0 else [int(x) for x in arr[:rank]]
+
+    assert p.left_target.decode() == ",".join(o.left_target)
+    assert p.right_target.decode() == ",".join(o.right_target)
+    assert p.result_gemm.decode() == ",".join(o.result_gemm)
+    assert (p.left_permtype, p.right_permtype, p.opA, p.opB) == (o.left_permtype, o.right_permtype, o.opA, o.opB)
+    assert perm(p.perm_left, p.left_rank) == o.perm_left
+    assert perm(p.perm_right, p.right_rank) == o.perm_right
+    assert perm(p.perm_result, p.result_rank) == o.perm_result
+    assert p.inner_rank == o.helper.num_contract_ranks
+
+
+def test_plan_contraction_rejects_bad_input(lib):
+    p = _lib.ContractionPlanC()
+    assert lib.tadev_plan_contraction(b"i,j", b"i,i", b"i,j", C.byref(p)) == _lib.EINVAL
+    assert lib.tadev_plan_contraction(b"i,z", b"i,k", b"k,j", C.byref(p)) == _lib.EINVAL
+    assert lib.tadev_plan_contraction(b"i", b"i,k", b"k,j", C.byref(p)) == _lib.EINVAL
+
+
+def _schedule(lib, Pr, Pc, r, c, Mt, Nt, Kt, a, b, cn, thr):
+    steps_k = (C.c_int32 * (Kt + 1))()
+    begin = (C.c_int32 * (Kt + 2))()
+    ns, npairs = C.c_int32(), C.c_int64()
+    cap = Mt * Nt * max(Kt, 1)
+    pi, pj = (C.c_int32 * max(cap, 1))(), (C.c_int32 * max(cap, 1))()
+
+    def ptr(x):
+        return x.ctypes.data_as(C.c_void_p) if x is not None else None
+
+    _lib.check(lib.tadev_summa_schedule(Pr, Pc, r, c, Mt, Nt, Kt, ptr(a), ptr(b), ptr(cn), thr, steps_k, begin,
+                                        C.byref(ns), pi, pj, cap, C.byref(npairs)))
+    out = []
+    for s in range(ns.value):
+        out.append((steps_k[s], [(pi[q], pj[q]) for q in range(begin[s], begin[s + 1])]))
+    return out
+
+
+@pytest.mark.parametrize("grid", [(1, 1), (1, 2), (2, 2), (4, 2), (3, 2)])
+@pytest.mark.parametrize("density", [1.0, 0.5, 0.1])
+def test_summa_schedule_matches_oracle(lib, grid, density):
+    """Steps (iterate_sparse, contraction_eval.h:974-1001) and tile-pair lists (contract,
+    :1311-1384) of every rank: product (C++) vs oracle, exact, including order."""
+    rng = np.random.default_rng(int(density * 100) + grid[0] * 7 + grid[1])
+    Mt, Nt, Kt = 11, 9, 13
+    thr = np.float32(0.5)
+    if density == 1.0:
+        a = b = cn = None
+        az = bz = cz = None
+    else:
+        a = np.where(rng.random((Mt, Kt)) < density, 1.0, 0.0).astype(np.float32)
+        b = np.where(rng.random((Kt, Nt)) < density, 1.0, 0.0).astype(np.float32)
+        cn = ((a @ b) > 0).astype(np.float32)
+        az, bz, cz = a < thr, b < thr, cn < thr
+    Pr, Pc = grid
+    total = 0
+    for r in range(Pr):
+        for c in range(Pc):
+            got = _schedule(lib, Pr, Pc, r, c, Mt, Nt, Kt, a, b, cn, float(thr))
+            want = O.summa_rank_schedule(Pr, Pc, r, c, Mt, Nt, Kt, az, bz, cz)
+            want = [(k, pairs) for (k, pairs) in want]
+            assert got == want
+            total += sum(len(p) for _, p in got)
+    if density == 1.0:
+        assert total == Mt * Nt * Kt
+    else:
+        assert total == int(((~az).astype(int) @ (~bz).astype(int)).sum())

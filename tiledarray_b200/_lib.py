@@ -106,6 +106,8 @@ PROTOTYPES = {
     "tadev_summa_f64": (_i, [_vp, _P(SummaPlanC), _P(SummaStatsC)]),
     "tadev_summa_schedule": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _P(C.c_int32), _vp, _vp,
                                   _i64, _P(_i64)]),
+    "tadev_summa_steps": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                               _P(C.c_int32)]),
     "tadev_probe_fp64_peak": (_i, [_vp, _i, _i, _P(_d), _P(_f)]),
     "tadev_probe_copy_gbs": (_i, [_vp, _sz, _i, _P(_d)]),
     "tadev_launch_count": (_i, [_vp, _P(_i64)]),

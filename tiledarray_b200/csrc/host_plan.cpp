@@ -263,3 +263,27 @@ extern "C" int tadev_summa_schedule(int Pr, int Pc, int r, int c, int Mt, int Nt
   }
   return TADEV_OK;
 }
+
+extern "C" int tadev_summa_steps(int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt, const float* a_norms,
+                                 const float* b_norms, const float* c_norms, float threshold, int32_t* step_k,
+                                 int32_t* step_flags, int32_t* a_begin, int32_t* a_rows, int32_t* b_begin,
+                                 int32_t* b_cols, int32_t* nsteps_out) {
+  TADEV_REQUIRE(Pr >= 1 && Pc >= 1 && r >= 0 && r < Pr && c >= 0 && c < Pc, "tadev_summa_steps: bad grid position");
+  TADEV_REQUIRE(Mt >= 0 && Nt >= 0 && Kt >= 0, "tadev_summa_steps: negative extents");
+  TADEV_REQUIRE(step_k && step_flags && a_begin && a_rows && b_begin && b_cols && nsteps_out, "tadev_summa_steps: null outputs");
+  SummaSchedule S = make_summa_schedule(Pr, Pc, r, c, Mt, Nt, Kt, a_norms, b_norms, c_norms, threshold);
+  int n = 0, na = 0, nb = 0;
+  for (auto& st : S.steps) {
+    step_k[n] = st.k;
+    step_flags[n] = (st.compute ? 1 : 0) | (st.bcast_a ? 2 : 0) | (st.bcast_b ? 4 : 0);
+    a_begin[n] = na;
+    b_begin[n] = nb;
+    for (int i : st.a_rows) a_rows[na++] = i;
+    for (int j : st.b_cols) b_cols[nb++] = j;
+    ++n;
+  }
+  a_begin[n] = na;
+  b_begin[n] = nb;
+  *nsteps_out = n;
+  return TADEV_OK;
+}

@@ -455,6 +455,8 @@ class ContEngine:
     """
 
     last_stats: Optional[ContractionStats] = None
+    depth = 0             # SUMMA pipeline depth in windows (0 = default 2; TA_SUMMA_MAX_DEPTH analogue)
+    steps_per_launch = 0  # K steps fused into one grouped-GEMM launch (0 = auto)
 
     def __init__(self, result: TsrExpr, left: TsrExpr, right: TsrExpr, factor: float):
         self.result, self.left, self.right, self.factor = result, left, right, factor
@@ -597,7 +599,7 @@ class ContEngine:
         sp.c_norms = c_n.ctypes.data_as(fp) if c_n is not None else None
         sp.threshold = thr
         sp.a_tiles, sp.b_tiles, sp.c_tiles = a_tab, b_tab, c_tab
-        sp.accumulate, sp.depth, sp.steps_per_launch = 0, 0, 0
+        sp.accumulate, sp.depth, sp.steps_per_launch = 0, ContEngine.depth, ContEngine.steps_per_launch
         st = SummaStatsC()
         check(w.lib.tadev_summa_f64(dev.ctx, C.byref(sp), C.byref(st)))
         stats.nsteps, stats.nsteps_skipped, stats.npairs = st.nsteps, st.nsteps_skipped, st.npairs
