@@ -468,8 +468,8 @@ class ContEngine:
         self.plan = plan
 
     @staticmethod
-    def _perm(arr) -> Optional[List[int]]:
-        return None if arr[0] < 0 else [int(x) for x in arr]
+    def _perm(arr, rank: int) -> Optional[List[int]]:
+        return None if arr[0] < 0 else [int(x) for x in arr[:rank]]
 
     def _permuted_operand(self, arr: DistArray, perm: Optional[List[int]]):
         """Explicit argument permutation (ArrayEvalImpl/LazyArrayTile + UnaryWrapper<Noop>,
@@ -502,8 +502,8 @@ class ContEngine:
         nc = P.inner_rank
         stats = ContractionStats()
         with dev.timer() as tperm:
-            trA, shA, tilesA, tmpA = self._permuted_operand(A, self._perm(P.perm_left))
-            trB, shB, tilesB, tmpB = self._permuted_operand(B, self._perm(P.perm_right))
+            trA, shA, tilesA, tmpA = self._permuted_operand(A, self._perm(P.perm_left, P.left_rank))
+            trB, shB, tilesB, tmpB = self._permuted_operand(B, self._perm(P.perm_right, P.right_rank))
         stats.permute_ms = tperm.ms if (tmpA or tmpB) else 0.0
 
         # fused (matrix) views: outer/inner mode ranges of each operand (GemmHelper, gemm_helper.h:62-98)
@@ -527,7 +527,7 @@ class ContEngine:
         Mt, Nt, Kt = len(m_ext), len(n_ext), len(k_ext)
 
         # result shape (make_shape, cont_engine.h:642-660)
-        perm_res = self._perm(P.perm_result)
+        perm_res = self._perm(P.perm_result, P.result_rank)
         sparse = not (shA.is_dense() and shB.is_dense())
         if sparse:
             _ta_assert(not shA.is_dense() and not shB.is_dense(), "mixed dense/sparse contraction is not supported")
