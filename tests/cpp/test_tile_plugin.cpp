@@ -1,0 +1,115 @@
+// C++ test of the tile plug-in (include/tadev.hpp) against known answers restated from the
+// reference's own tests:
+//   tests/tile_op_contract_reduce.cpp:109-220  integer tiles, factor 3, NN/TN/NT/TT, accumulate
+//   tests/librett.cpp:594-661                   rank-4 permutations {0,3,2,1} and {1,0,3,2}
+//   contract_reduce.h:397-398                   add_to merge
+// Build: g++ -std=c++17 -I include tests/cpp/test_tile_plugin.cpp -L tiledarray_b200 -ltadev
+// Runs on a GPU box only (tests/test_gpu_cpp_plugin.py).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "tadev.hpp"
+
+static int failures = 0;
+#define CHECK(cond)                                                     \
+  do {                                                                  \
+    if (!(cond)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #cond); ++failures; } \
+  } while (0)
+
+using tadev::GemmHelper;
+using tadev::Op;
+using tadev::Tile;
+
+static std::vector<double> int_matrix(int rows, int cols, unsigned seed) {
+  std::vector<double> v((size_t)rows * cols);
+  unsigned s = seed;
+  for (auto& x : v) { s = s * 1664525u + 1013904223u; x = (double)((s >> 8) % 101); }
+  return v;
+}
+static std::vector<double> transpose(const std::vector<double>& a, int rows, int cols) {
+  std::vector<double> t(a.size());
+  for (int i = 0; i < rows; ++i) for (int j = 0; j < cols; ++j) t[(size_t)j * rows + i] = a[(size_t)i * cols + j];
+  return t;
+}
+
+int main() {
+  tadev::Context ctx(0);
+  const int m = 18, n = 36, k = 27;
+  const auto A = int_matrix(m, k, 1), B = int_matrix(k, n, 2);
+  const auto AT = transpose(A, m, k), BT = transpose(B, k, n);
+  std::vector<double> ref((size_t)m * n, 0.0);
+  for (int i = 0; i < m; ++i) for (int j = 0; j < n; ++j) { double s = 0; for (int x = 0; x < k; ++x) s += A[(size_t)i * k + x] * B[(size_t)x * n + j]; ref[(size_t)i * n + j] = 3 * s; }
+
+  for (int ta = 0; ta < 2; ++ta)
+    for (int tb = 0; tb < 2; ++tb) {
+      Tile left(ctx, ta ? tadev::Range{k, m} : tadev::Range{m, k}), right(ctx, tb ? tadev::Range{n, k} : tadev::Range{k, n});
+      left.from_host(ta ? AT.data() : A.data());
+      right.from_host(tb ? BT.data() : B.data());
+      GemmHelper h(ta ? Op::Trans : Op::NoTrans, tb ? Op::Trans : Op::NoTrans, 2u, 2u, 2u);
+      Tile result;                       // empty: first op(result, left, right) seeds it
+      gemm(result, left, right, 3, h);
+      std::vector<double> got((size_t)m * n);
+      result.to_host(got.data());
+      bool ok = true;
+      for (size_t i = 0; i < got.size(); ++i) ok = ok && got[i] == ref[i];
+      CHECK(ok);
+      gemm(result, left, right, 3, h);   // second application accumulates
+      result.to_host(got.data());
+      ok = true;
+      for (size_t i = 0; i < got.size(); ++i) ok = ok && got[i] == 2 * ref[i];
+      CHECK(ok);
+      Tile fresh = gemm(left, right, 3, h);
+      add_to(fresh, result);             // partial-result merge
+      fresh.to_host(got.data());
+      ok = true;
+      for (size_t i = 0; i < got.size(); ++i) ok = ok && got[i] == 3 * ref[i];
+      CHECK(ok);
+    }
+
+  // congruence violation -> exception (TA_ASSERT analogue)
+  {
+    Tile l(ctx, {4, 5}), r(ctx, {6, 3});
+    bool threw = false;
+    try { (void)gemm(l, r, 1.0, GemmHelper(Op::NoTrans, Op::NoTrans, 2u, 2u, 2u)); } catch (const tadev::Exception&) { threw = true; }
+    CHECK(threw);
+  }
+
+  // rank-4 permutations, tests/librett.cpp:594-661
+  {
+    const int64_t a = 2, b = 3, c = 6, d = 4;
+    std::vector<double> in((size_t)(a * b * c * d));
+    for (size_t i = 0; i < in.size(); ++i) in[i] = (double)i;
+    Tile ta_(ctx, {a, b, c, d});
+    ta_.from_host(in.data());
+    {
+      Tile tb_ = permute(ta_, {0, 3, 2, 1});  // b(i,l,k,j) = a(i,j,k,l)
+      CHECK((tb_.range() == tadev::Range{a, d, c, b}));
+      std::vector<double> out(in.size());
+      tb_.to_host(out.data());
+      size_t it = 0; bool ok = true;
+      for (int64_t i = 0; i < a; ++i) for (int64_t j = 0; j < b; ++j) for (int64_t kk = 0; kk < c; ++kk) for (int64_t l = 0; l < d; ++l, ++it)
+        ok = ok && out[(size_t)(((i * d + l) * c + kk) * b + j)] == (double)it;
+      CHECK(ok);
+    }
+    {
+      Tile tb_ = permute(ta_, {1, 0, 3, 2});  // b(j,i,l,k) = a(i,j,k,l)
+      std::vector<double> out(in.size());
+      tb_.to_host(out.data());
+      size_t it = 0; bool ok = true;
+      for (int64_t i = 0; i < a; ++i) for (int64_t j = 0; j < b; ++j) for (int64_t kk = 0; kk < c; ++kk) for (int64_t l = 0; l < d; ++l, ++it)
+        ok = ok && out[(size_t)(((j * a + i) * d + l) * c + kk)] == (double)it;
+      CHECK(ok);
+    }
+    Tile cl = clone(ta_);
+    scale_to(cl, 2.0);
+    std::vector<double> out(in.size());
+    cl.to_host(out.data());
+    bool ok = true;
+    for (size_t i = 0; i < in.size(); ++i) ok = ok && out[i] == 2.0 * in[i];
+    CHECK(ok);
+  }
+  ctx.sync();
+  std::printf(failures ? "CPP_PLUGIN FAILED (%d)\n" : "CPP_PLUGIN OK\n", failures);
+  return failures ? 1 : 0;
+}
