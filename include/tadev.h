@@ -120,6 +120,12 @@ int tadev_gemm_f64(tadev_ctx* ctx, tadev_stream s, int opA, int opB, int m, int 
  * elem_bytes in {4, 8, 16}. */
 int tadev_permute(tadev_ctx* ctx, tadev_stream s, int rank, const int64_t* extent,
                   const int32_t* perm, int elem_bytes, const void* d_in, void* d_out);
+/* Same permutation applied to `ntiles` tiles of identical extents in ONE launch (every tile of a
+ * contraction operand gets the same permutation: dist_eval/array_eval.h:42,170). h_in / h_out are
+ * HOST arrays of device pointers. */
+int tadev_permute_batched(tadev_ctx* ctx, tadev_stream s, int rank, const int64_t* extent,
+                          const int32_t* perm, int elem_bytes, int ntiles, const void* const* h_in,
+                          void* const* h_out);
 /* result(+)= arg: ContractReduce partial-result merge (contract_reduce.h:397-398; GPU ref
  * device/btas_um_tensor.h:377-384 axpy). */
 int tadev_add_to_f64(tadev_ctx* ctx, tadev_stream s, size_t n, double* d_result, const double* d_arg);

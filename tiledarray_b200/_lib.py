@@ -88,6 +88,7 @@ PROTOTYPES = {
     "tadev_gemm_grouped_f64_dev": (_i, [_vp, _vp, _i, _i, _d, _vp, _i, _vp, _vp, _i]),
     "tadev_gemm_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _d, _vp]),
     "tadev_permute": (_i, [_vp, _vp, _i, _P(_i64), _P(C.c_int32), _i, _vp, _vp]),
+    "tadev_permute_batched": (_i, [_vp, _vp, _i, _P(_i64), _P(C.c_int32), _i, _i, _P(_vp), _P(_vp)]),
     "tadev_add_to_f64": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "tadev_scale_f64": (_i, [_vp, _vp, _sz, _vp, _d]),
     "tadev_tile_sqnorms_f64": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),

@@ -12,6 +12,9 @@
 //   3. otherwise                       -> shared-memory tiled transpose over (a, b) where a is the
 //      input-fastest mode and b the output-fastest mode; global reads are coalesced along a,
 //      global writes along b, smem rows are padded by one element (conflict-free both ways).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.h"
 
 namespace {
@@ -29,16 +32,19 @@ struct PermParams {
   int nother;            // number of remaining modes
   int other[MAXR];       // their input-mode indices, fastest varying first
   int64_t total;         // total elements
-  // row-copy
-  int64_t row_len;       // elements per preserved row (already divided by vec)
+  int64_t row_len;       // row copy: elements per preserved row (already divided by the vector width)
   int64_t nrows;
 };
 
+// blockIdx.y selects the tile of a batch (all tiles of a batch share extents and permutation).
 template <typename T>
-__global__ void __launch_bounds__(256) transpose_tiled_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                              PermParams p) {
+__global__ void __launch_bounds__(256) transpose_tiled_kernel(const T* __restrict__ in0, T* __restrict__ out0,
+                                                              const void* const* __restrict__ ins,
+                                                              void* const* __restrict__ outs, PermParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);
+  const T* __restrict__ in = ins ? static_cast<const T*>(ins[blockIdx.y]) : in0;
+  T* __restrict__ out = outs ? static_cast<T*>(outs[blockIdx.y]) : out0;
   const int TA = p.TA, TB = p.TB;
   const int ldt = TA + 1;
   int64_t bid = blockIdx.x;
@@ -53,29 +59,35 @@ __global__ void __launch_bounds__(256) transpose_tiled_kernel(const T* __restric
     base_out += i * p.sout[m];
   }
   const int64_t a0 = ta * TA, b0 = tb * TB;
-  const int64_t ea = p.ext[p.a], eb = p.ext[p.b];
+  const int ra = (int)min((int64_t)TA, p.ext[p.a] - a0);  // valid extent of this tile along a / b
+  const int rb = (int)min((int64_t)TB, p.ext[p.b] - b0);
   const int64_t sin_b = p.sin[p.b], sout_a = p.sout[p.a];
-  const int la = 31 - __clz(TA);  // log2
-  const int lb = 31 - __clz(TB);
+  const T* __restrict__ src = in + base_in + b0 * sin_b + a0;
+  T* __restrict__ dst = out + base_out + a0 * sout_a + b0;
+  const int la = 31 - __clz(TA), lb = 31 - __clz(TB);
   const int n = TA * TB;
   // read: consecutive threads walk the input-fastest mode a
-#pragma unroll 4
+#pragma unroll 8
   for (int idx = threadIdx.x; idx < n; idx += 256) {
     const int ia = idx & (TA - 1), ib = idx >> la;
-    if (a0 + ia < ea && b0 + ib < eb) tile[ib * ldt + ia] = in[base_in + (b0 + ib) * sin_b + (a0 + ia)];
+    if (ia < ra && ib < rb) tile[ib * ldt + ia] = src[(int64_t)ib * sin_b + ia];
   }
   __syncthreads();
   // write: consecutive threads walk the output-fastest mode b
-#pragma unroll 4
+#pragma unroll 8
   for (int idx = threadIdx.x; idx < n; idx += 256) {
     const int ib = idx & (TB - 1), ia = idx >> lb;
-    if (a0 + ia < ea && b0 + ib < eb) out[base_out + (a0 + ia) * sout_a + (b0 + ib)] = tile[ib * ldt + ia];
+    if (ia < ra && ib < rb) dst[(int64_t)ia * sout_a + ib] = tile[ib * ldt + ia];
   }
 }
 
 // Rows (the preserved, contiguous last mode) are copied whole; V is the vector type.
 template <typename V>
-__global__ void __launch_bounds__(256) rowcopy_kernel(const V* __restrict__ in, V* __restrict__ out, PermParams p) {
+__global__ void __launch_bounds__(256) rowcopy_kernel(const V* __restrict__ in0, V* __restrict__ out0,
+                                                      const void* const* __restrict__ ins,
+                                                      void* const* __restrict__ outs, PermParams p) {
+  const V* __restrict__ in = ins ? static_cast<const V*>(ins[blockIdx.y]) : in0;
+  V* __restrict__ out = outs ? static_cast<V*>(outs[blockIdx.y]) : out0;
   const int64_t total = p.nrows * p.row_len;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += stride) {
@@ -100,41 +112,20 @@ int64_t pow2_ceil(int64_t x) {
   return r;
 }
 
-template <typename T>
-int launch_tiled(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const void* in, void* out) {
-  int64_t blocks = p.nTa * p.nTb;
-  for (int d = 0; d < p.nother; ++d) blocks *= p.ext[p.other[d]];
-  TADEV_REQUIRE(blocks < (1ll << 31), "tadev_permute: tile too large for one launch");
-  const size_t smem = sizeof(T) * (size_t)(p.TA + 1) * p.TB;
-  transpose_tiled_kernel<T><<<(unsigned)blocks, 256, smem, s>>>((const T*)in, (T*)out, p);
-  ctx->launches++;
-  TADEV_CHECK_CUDA(cudaGetLastError());
-  return TADEV_OK;
-}
+enum PlanKind { kCopy = 0, kRowCopy = 1, kTiled = 2 };
+struct Plan {
+  PlanKind kind;
+  PermParams p;
+  int64_t total;
+  int elem_bytes;
+  bool row_vec16_possible;  // row bytes % 16 == 0 (pointer alignment is checked per tile)
+};
 
-template <typename V>
-int launch_rowcopy(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const void* in, void* out) {
-  const int64_t total = p.nrows * p.row_len;
-  int64_t blocks = ceil_div64(total, 256 * 4);
-  const int64_t maxb = (int64_t)ctx->num_sms * 32;
-  if (blocks > maxb) blocks = maxb;
-  if (blocks < 1) blocks = 1;
-  rowcopy_kernel<V><<<(unsigned)blocks, 256, 0, s>>>((const V*)in, (V*)out, p);
-  ctx->launches++;
-  TADEV_CHECK_CUDA(cudaGetLastError());
-  return TADEV_OK;
-}
-
-}  // namespace
-
-extern "C" int tadev_permute(tadev_ctx* ctx, tadev_stream s_, int rank, const int64_t* extent,
-                             const int32_t* perm, int elem_bytes, const void* d_in, void* d_out) {
-  TADEV_REQUIRE(ctx, "tadev_permute: null ctx");
+// Host planning shared by the single-tile and the batched entry.
+int plan_permute(int rank, const int64_t* extent, const int32_t* perm, int elem_bytes, Plan* plan) {
   TADEV_REQUIRE(rank >= 0 && rank <= 16, "tadev_permute: rank %d unsupported", rank);
   TADEV_REQUIRE(elem_bytes == 4 || elem_bytes == 8 || elem_bytes == 16, "tadev_permute: elem_bytes %d", elem_bytes);
   TADEV_REQUIRE(rank == 0 || (extent && perm), "tadev_permute: null extent/perm");
-  cudaStream_t s = (cudaStream_t)s_;
-  // validate the permutation
   {
     uint32_t seen = 0;
     for (int i = 0; i < rank; ++i) {
@@ -145,10 +136,11 @@ extern "C" int tadev_permute(tadev_ctx* ctx, tadev_stream s_, int rank, const in
   }
   int64_t total = 1;
   for (int i = 0; i < rank; ++i) total *= extent[i];
+  plan->total = total;
+  plan->elem_bytes = elem_bytes;
+  plan->kind = kCopy;
+  plan->row_vec16_possible = false;
   if (total == 0) return TADEV_OK;
-  TADEV_REQUIRE(d_in && d_out, "tadev_permute: null tile");
-  TADEV_REQUIRE(d_in != d_out, "tadev_permute: in-place permutation is not supported");
-
   // output strides per output mode
   int64_t out_ext[16], out_stride[16];
   for (int i = 0; i < rank; ++i) out_ext[perm[i]] = extent[i];
@@ -156,34 +148,22 @@ extern "C" int tadev_permute(tadev_ctx* ctx, tadev_stream s_, int rank, const in
     int64_t st = 1;
     for (int j = rank - 1; j >= 0; --j) { out_stride[j] = st; st *= out_ext[j]; }
   }
-  // reduce: drop unit modes, fuse input modes i,i+1 with perm[i+1] == perm[i]+1
+  // reduce: drop unit modes; fuse input modes that stay adjacent and ordered in the output
   int R = 0;
   int64_t ext[16], sout[16];
   for (int i = 0; i < rank; ++i) {
     if (extent[i] == 1) continue;
-    ext[R] = extent[i];
-    sout[R] = out_stride[perm[i]];
-    ++R;
-  }
-  // fuse: mode j+1 follows mode j contiguously in the output iff sout[j] == sout[j+1]*ext[j+1]
-  {
-    int W = 0;
-    for (int i = 0; i < R; ++i) {
-      if (W > 0 && sout[W - 1] == sout[i] * ext[i]) {
-        ext[W - 1] *= ext[i];
-        sout[W - 1] = sout[i];
-      } else {
-        ext[W] = ext[i]; sout[W] = sout[i]; ++W;
-      }
+    if (R > 0 && sout[R - 1] == out_stride[perm[i]] * extent[i]) {
+      ext[R - 1] *= extent[i];
+      sout[R - 1] = out_stride[perm[i]];
+    } else {
+      ext[R] = extent[i]; sout[R] = out_stride[perm[i]]; ++R;
     }
-    R = W;
   }
-  if (R <= 1) {  // identity
-    TADEV_CHECK_CUDA(cudaMemcpyAsync(d_out, d_in, (size_t)total * elem_bytes, cudaMemcpyDeviceToDevice, s));
-    return TADEV_OK;
-  }
+  if (R <= 1) return TADEV_OK;  // identity
   TADEV_REQUIRE(R <= MAXR, "tadev_permute: reduced rank %d > %d", R, MAXR);
-  PermParams p{};
+  PermParams& p = plan->p;
+  p = PermParams{};
   p.R = R;
   p.total = total;
   {
@@ -192,6 +172,7 @@ extern "C" int tadev_permute(tadev_ctx* ctx, tadev_stream s_, int rank, const in
   }
   if (p.sout[R - 1] == 1) {
     // last mode preserved: row copy. Enumerate rows in OUTPUT order: sort the other modes by sout.
+    plan->kind = kRowCopy;
     int idx[MAXR], n = 0;
     for (int i = 0; i < R - 1; ++i) idx[n++] = i;
     for (int i = 0; i < n; ++i)
@@ -199,43 +180,143 @@ extern "C" int tadev_permute(tadev_ctx* ctx, tadev_stream s_, int rank, const in
         if (p.sout[idx[j]] < p.sout[idx[i]]) { int tswap = idx[i]; idx[i] = idx[j]; idx[j] = tswap; }
     p.nother = n;
     for (int i = 0; i < n; ++i) p.other[i] = idx[i];
-    const int64_t L = p.ext[R - 1];
-    p.nrows = total / L;
-    const int64_t row_bytes = L * elem_bytes;
-    const bool al16 = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
-    if (al16) {
-      const int vec = 16 / elem_bytes;
-      p.row_len = L / vec;
-      for (int i = 0; i < R - 1; ++i) p.sin[i] /= vec;
-      return launch_rowcopy<uint4>(ctx, s, p, d_in, d_out);
-    }
-    p.row_len = L;
-    if (elem_bytes == 4) return launch_rowcopy<uint32_t>(ctx, s, p, d_in, d_out);
-    if (elem_bytes == 8) return launch_rowcopy<uint64_t>(ctx, s, p, d_in, d_out);
-    return launch_rowcopy<uint4>(ctx, s, p, d_in, d_out);
+    p.row_len = p.ext[R - 1];
+    p.nrows = total / p.row_len;
+    plan->row_vec16_possible = (p.row_len * elem_bytes) % 16 == 0;
+    return TADEV_OK;
   }
   // general: tiled transpose over a = R-1 and b = the mode with sout == 1
+  plan->kind = kTiled;
   p.a = R - 1;
   p.b = -1;
   for (int i = 0; i < R; ++i)
     if (p.sout[i] == 1) p.b = i;
   TADEV_REQUIRE(p.b >= 0 && p.b != p.a, "tadev_permute: internal planning error");
-  // tile: ~2048 elements; give the short mode its full (power-of-two padded) extent
-  int64_t TB = pow2_ceil(p.ext[p.b]); if (TB > 32) TB = 32;
-  int64_t TA = pow2_ceil(p.ext[p.a]); if (TA > 2048 / TB) TA = 2048 / TB;
-  if (TA < 32) { // a is short: widen b instead
-    TB = pow2_ceil(p.ext[p.b]); if (TB > 2048 / TA) TB = 2048 / TA;
-  }
+  // tile: up to 4096 elements (<= 32 KiB of 8-byte elements); 64 x 64 when both modes are long,
+  // otherwise the short mode gets its full (power-of-two padded) extent and the other widens
+  int64_t budget = elem_bytes == 16 ? 2048 : 4096;
+  static const char* env = getenv("TADEV_PERM_TILE");  // "TAxTB" override for experiments
+  int64_t TA = 64, TB = 64;
+  if (env && sscanf(env, "%ldx%ld", &TA, &TB) == 2) { budget = TA * TB; }
+  TB = std::min<int64_t>(pow2_ceil(p.ext[p.b]), TB);
+  TA = std::min<int64_t>(pow2_ceil(p.ext[p.a]), budget / TB);
+  if (TA * TB < budget) TB = std::min<int64_t>(pow2_ceil(p.ext[p.b]), budget / TA);
   p.TA = (int)TA; p.TB = (int)TB;
   p.nTa = ceil_div64(p.ext[p.a], TA);
   p.nTb = ceil_div64(p.ext[p.b], TB);
   p.nother = 0;
   for (int i = R - 2; i >= 0; --i)
     if (i != p.b) p.other[p.nother++] = i;
-  if (elem_bytes == 4) return launch_tiled<uint32_t>(ctx, s, p, d_in, d_out);
-  if (elem_bytes == 8) return launch_tiled<uint64_t>(ctx, s, p, d_in, d_out);
-  return launch_tiled<uint4>(ctx, s, p, d_in, d_out);
+  return TADEV_OK;
+}
+
+template <typename T>
+int launch_tiled(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const void* in, void* out,
+                 const void* const* d_ins, void* const* d_outs, int ntiles) {
+  int64_t blocks = p.nTa * p.nTb;
+  for (int d = 0; d < p.nother; ++d) blocks *= p.ext[p.other[d]];
+  TADEV_REQUIRE(blocks < (1ll << 31), "tadev_permute: tile too large for one launch");
+  const size_t smem = sizeof(T) * (size_t)(p.TA + 1) * p.TB;
+  auto kern = transpose_tiled_kernel<T>;
+  if (smem > 48 * 1024) TADEV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3((unsigned)blocks, (unsigned)ntiles), 256, smem, s>>>((const T*)in, (T*)out, d_ins, d_outs, p);
+  ctx->launches++;
+  TADEV_CHECK_CUDA(cudaGetLastError());
+  return TADEV_OK;
+}
+
+template <typename V>
+int launch_rowcopy(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const void* in, void* out,
+                   const void* const* d_ins, void* const* d_outs, int ntiles) {
+  const int64_t total = p.nrows * p.row_len;
+  int64_t blocks = ceil_div64(total, 256 * 4);
+  const int64_t maxb = std::max<int64_t>(1, (int64_t)ctx->num_sms * 32 / ntiles);
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  rowcopy_kernel<V><<<dim3((unsigned)blocks, (unsigned)ntiles), 256, 0, s>>>((const V*)in, (V*)out, d_ins, d_outs, p);
+  ctx->launches++;
+  TADEV_CHECK_CUDA(cudaGetLastError());
+  return TADEV_OK;
+}
+
+int launch_plan(tadev_ctx* ctx, cudaStream_t s, Plan& plan, bool ptrs_al16, const void* in, void* out,
+                const void* const* d_ins, void* const* d_outs, int ntiles) {
+  PermParams p = plan.p;
+  const int eb = plan.elem_bytes;
+  if (plan.kind == kRowCopy) {
+    if (plan.row_vec16_possible && ptrs_al16) {
+      const int vec = 16 / eb;
+      p.row_len /= vec;
+      for (int i = 0; i < p.R - 1; ++i) p.sin[i] /= vec;
+      return launch_rowcopy<uint4>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
+    }
+    if (eb == 4) return launch_rowcopy<uint32_t>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
+    if (eb == 8) return launch_rowcopy<uint64_t>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
+    return launch_rowcopy<uint4>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
+  }
+  if (eb == 4) return launch_tiled<uint32_t>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
+  if (eb == 8) return launch_tiled<uint64_t>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
+  return launch_tiled<uint4>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
+}
+
+}  // namespace
+
+extern "C" int tadev_permute(tadev_ctx* ctx, tadev_stream s_, int rank, const int64_t* extent,
+                             const int32_t* perm, int elem_bytes, const void* d_in, void* d_out) {
+  TADEV_REQUIRE(ctx, "tadev_permute: null ctx");
+  cudaStream_t s = (cudaStream_t)s_;
+  Plan plan;
+  int rc = plan_permute(rank, extent, perm, elem_bytes, &plan);
+  if (rc) return rc;
+  if (plan.total == 0) return TADEV_OK;
+  TADEV_REQUIRE(d_in && d_out, "tadev_permute: null tile");
+  TADEV_REQUIRE(d_in != d_out, "tadev_permute: in-place permutation is not supported");
+  if (plan.kind == kCopy) {
+    TADEV_CHECK_CUDA(cudaMemcpyAsync(d_out, d_in, (size_t)plan.total * elem_bytes, cudaMemcpyDeviceToDevice, s));
+    return TADEV_OK;
+  }
+  const bool al16 = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+  return launch_plan(ctx, s, plan, al16, d_in, d_out, nullptr, nullptr, 1);
+}
+
+// Many tiles with identical extents and permutation in ONE launch (the argument-tile permutes of a
+// contraction, dist_eval/array_eval.h:42,170: every tile of an operand gets the same permutation).
+extern "C" int tadev_permute_batched(tadev_ctx* ctx, tadev_stream s_, int rank, const int64_t* extent,
+                                     const int32_t* perm, int elem_bytes, int ntiles, const void* const* h_in,
+                                     void* const* h_out) {
+  TADEV_REQUIRE(ctx, "tadev_permute_batched: null ctx");
+  TADEV_REQUIRE(ntiles >= 0, "tadev_permute_batched: negative tile count");
+  if (ntiles == 0) return TADEV_OK;
+  TADEV_REQUIRE(h_in && h_out, "tadev_permute_batched: null pointer arrays");
+  cudaStream_t s = (cudaStream_t)s_;
+  Plan plan;
+  int rc = plan_permute(rank, extent, perm, elem_bytes, &plan);
+  if (rc) return rc;
+  if (plan.total == 0) return TADEV_OK;
+  bool al16 = true;
+  for (int i = 0; i < ntiles; ++i) {
+    TADEV_REQUIRE(h_in[i] && h_out[i] && h_in[i] != h_out[i], "tadev_permute_batched: tile %d null or in place", i);
+    al16 = al16 && (((reinterpret_cast<uintptr_t>(h_in[i]) | reinterpret_cast<uintptr_t>(h_out[i])) & 15) == 0);
+  }
+  if (plan.kind == kCopy) {
+    for (int i = 0; i < ntiles; ++i)
+      TADEV_CHECK_CUDA(cudaMemcpyAsync(h_out[i], h_in[i], (size_t)plan.total * elem_bytes, cudaMemcpyDeviceToDevice, s));
+    return TADEV_OK;
+  }
+  for (int first = 0; first < ntiles; first += 32768) {  // gridDim.y limit
+    const int n = std::min(32768, ntiles - first);
+    void *h = nullptr, *d = nullptr;
+    cudaEvent_t done;
+    rc = tadev_stage(ctx, s, sizeof(void*) * 2 * (size_t)n, &h, &d, &done);
+    if (rc) return rc;
+    memcpy(h, h_in + first, sizeof(void*) * n);
+    memcpy((char*)h + sizeof(void*) * n, h_out + first, sizeof(void*) * n);
+    TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, sizeof(void*) * 2 * (size_t)n, cudaMemcpyHostToDevice, s));
+    rc = launch_plan(ctx, s, plan, al16, nullptr, nullptr, (const void* const*)d, (void* const*)((char*)d + sizeof(void*) * n), n);
+    TADEV_CHECK_CUDA(cudaEventRecord(done, s));
+    if (rc) return rc;
+  }
+  return TADEV_OK;
 }
 
 // ---- small elementwise helpers on the contraction path -------------------------------------

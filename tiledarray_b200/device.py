@@ -163,6 +163,16 @@ class Device:
         pm = (C.c_int32 * max(rank, 1))(*perm)
         check(self.lib.tadev_permute(self.ctx, stream or self.stream, rank, ext, pm, elem_bytes, src.ptr, dst.ptr))
 
+    def permute_batched(self, extent: Sequence[int], perm: Sequence[int], elem_bytes: int,
+                        srcs: Sequence[DeviceBuffer], dsts: Sequence[DeviceBuffer], stream=None) -> None:
+        """One launch for many tiles of identical extents (tadev_permute_batched)."""
+        rank, n = len(extent), len(srcs)
+        ext = (C.c_int64 * max(rank, 1))(*extent)
+        pm = (C.c_int32 * max(rank, 1))(*perm)
+        ins = (C.c_void_p * max(n, 1))(*[b.ptr for b in srcs])
+        outs = (C.c_void_p * max(n, 1))(*[b.ptr for b in dsts])
+        check(self.lib.tadev_permute_batched(self.ctx, stream or self.stream, rank, ext, pm, elem_bytes, n, ins, outs))
+
     def add_to(self, n: int, result: DeviceBuffer, arg: DeviceBuffer, stream=None) -> None:
         check(self.lib.tadev_add_to_f64(self.ctx, stream or self.stream, n, result.ptr, arg.ptr))
 

@@ -481,18 +481,27 @@ class ContEngine:
             dims[p] = arr.trange.dims[i]
         tr = TiledRange(dims)
         shape = arr.shape.perm(perm) if not arr.shape.is_dense() else arr.shape
-        tiles, temps = {}, []
+        # one arena for all permuted tiles; one batched launch per distinct tile extent
+        tiles: Dict[int, DeviceBuffer] = {}
+        sizes = {o: (buf.nbytes // 8 + 1) & ~1 for o, buf in arr.tiles.items()}
+        arena = self.dev.alloc(max(sum(sizes.values()), 2) * 8)
+        by_extent: Dict[Tuple[int, ...], Tuple[list, list]] = {}
+        off = 0
         for o, buf in arr.tiles.items():
             idx = arr.trange.tile_index(o)
             ext = arr.trange.tile_extent(idx)
             pidx = [0] * len(perm)
             for i, p in enumerate(perm):
                 pidx[p] = idx[i]
-            dst = self.dev.alloc(buf.nbytes)
-            self.dev.permute(ext, perm, 8, buf, dst)
+            dst = arena.view(off * 8, buf.nbytes)
+            off += sizes[o]
+            srcs, dsts = by_extent.setdefault(tuple(ext), ([], []))
+            srcs.append(buf)
+            dsts.append(dst)
             tiles[tr.tile_ordinal(pidx)] = dst
-            temps.append(dst)
-        return tr, shape, tiles, temps
+        for ext, (srcs, dsts) in by_extent.items():
+            self.dev.permute_batched(ext, perm, 8, srcs, dsts)
+        return tr, shape, tiles, [arena]
 
     def eval(self) -> ContractionStats:
         P, w, dev = self.plan, self.world, self.dev
@@ -623,6 +632,7 @@ class ContEngine:
             with dev.timer() as tp2:
                 out_arena = dev.alloc(arena.nbytes)
                 off = 0
+                by_extent: Dict[Tuple[int, ...], Tuple[list, list]] = {}
                 for (i, j), s in zip(local_c, sizes):
                     o = i * Nt + j
                     idx = tr_gemm.tile_index(o)
@@ -631,9 +641,13 @@ class ContEngine:
                     for a_, p in enumerate(perm_res):
                         pidx[p] = idx[a_]
                     dst = out_arena.view(off * 8, gemm_tiles[o].nbytes)
-                    dev.permute(ext, perm_res, 8, gemm_tiles[o], dst)
+                    srcs, dsts = by_extent.setdefault(tuple(ext), ([], []))
+                    srcs.append(gemm_tiles[o])
+                    dsts.append(dst)
                     Cres.tiles[tr_target.tile_ordinal(pidx)] = dst
                     off += s
+                for ext, (srcs, dsts) in by_extent.items():
+                    dev.permute_batched(ext, perm_res, 8, srcs, dsts)
             stats.permute_ms += tp2.ms
             arena.free()
             Cres._arena = out_arena
