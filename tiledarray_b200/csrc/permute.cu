@@ -81,28 +81,50 @@ __global__ void __launch_bounds__(256) transpose_tiled_kernel(const T* __restric
   }
 }
 
-// Rows (the preserved, contiguous last mode) are copied whole; V is the vector type.
-template <typename V>
+// Rows (the preserved, contiguous last mode) are copied whole; V is the vector type, I the index
+// type (32-bit whenever the tile has < 2^31 vector elements: 64-bit div/mod costs ~10x more).
+// Each thread moves 4 independent chunks per iteration (loads first, then stores).
+template <typename V, typename I>
 __global__ void __launch_bounds__(256) rowcopy_kernel(const V* __restrict__ in0, V* __restrict__ out0,
                                                       const void* const* __restrict__ ins,
                                                       void* const* __restrict__ outs, PermParams p) {
   const V* __restrict__ in = ins ? static_cast<const V*>(ins[blockIdx.y]) : in0;
   V* __restrict__ out = outs ? static_cast<V*>(outs[blockIdx.y]) : out0;
-  const int64_t total = p.nrows * p.row_len;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += stride) {
-    int64_t row = q / p.row_len;
-    const int64_t c = q - row * p.row_len;
+  const I row_len = (I)p.row_len;
+  const I total = (I)(p.nrows * p.row_len);
+  const I stride = (I)gridDim.x * (I)blockDim.x;
+  I ext[MAXR], sin[MAXR];
+#pragma unroll
+  for (int d = 0; d < MAXR; ++d) { const int m = d < p.nother ? p.other[d] : 0; ext[d] = (I)p.ext[m]; sin[d] = (I)p.sin[m]; }
+  const int nother = p.nother;
+  auto src_of = [&](I q) -> I {
+    I row = q / row_len;
+    const I c = q - row * row_len;
     // q enumerates the OUTPUT in order: decompose the output row ordinal into output-mode
     // indices. other[] lists the non-row modes by increasing output stride.
-    int64_t off_in = 0;
-    for (int d = 0; d < p.nother; ++d) {
-      const int m = p.other[d];
-      const int64_t i = row % p.ext[m];
-      row /= p.ext[m];
-      off_in += i * p.sin[m];
+    I off_in = c;
+#pragma unroll
+    for (int d = 0; d < MAXR; ++d) {
+      if (d < nother) {
+        const I nxt = row / ext[d];
+        off_in += (row - nxt * ext[d]) * sin[d];
+        row = nxt;
+      }
     }
-    out[q] = in[off_in + c];  // sin[] pre-divided by the vector width for the row mode
+    return off_in;
+  };
+  for (I q = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; q < total; q += 4 * stride) {
+    V v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const I qq = q + (I)u * stride;
+      if (qq < total) v[u] = in[src_of(qq)];  // sin[] pre-divided by the vector width for the row mode
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const I qq = q + (I)u * stride;
+      if (qq < total) out[qq] = v[u];
+    }
   }
 }
 
@@ -194,9 +216,9 @@ int plan_permute(int rank, const int64_t* extent, const int32_t* perm, int elem_
   TADEV_REQUIRE(p.b >= 0 && p.b != p.a, "tadev_permute: internal planning error");
   // tile: up to 4096 elements (<= 32 KiB of 8-byte elements); 64 x 64 when both modes are long,
   // otherwise the short mode gets its full (power-of-two padded) extent and the other widens
-  int64_t budget = elem_bytes == 16 ? 2048 : 4096;
+  int64_t budget = 2048;
   static const char* env = getenv("TADEV_PERM_TILE");  // "TAxTB" override for experiments
-  int64_t TA = 64, TB = 64;
+  int64_t TA = 64, TB = 32;  // measured best on B200: 4.85 TB/s vs 4.3 for 64x64 (profiles/r01_permute_*.json)
   if (env && sscanf(env, "%ldx%ld", &TA, &TB) == 2) { budget = TA * TB; }
   TB = std::min<int64_t>(pow2_ceil(p.ext[p.b]), TB);
   TA = std::min<int64_t>(pow2_ceil(p.ext[p.a]), budget / TB);
@@ -230,10 +252,13 @@ int launch_rowcopy(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const vo
                    const void* const* d_ins, void* const* d_outs, int ntiles) {
   const int64_t total = p.nrows * p.row_len;
   int64_t blocks = ceil_div64(total, 256 * 4);
-  const int64_t maxb = std::max<int64_t>(1, (int64_t)ctx->num_sms * 32 / ntiles);
+  const int64_t maxb = std::max<int64_t>(1, (int64_t)ctx->num_sms * 16 / ntiles);
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
-  rowcopy_kernel<V><<<dim3((unsigned)blocks, (unsigned)ntiles), 256, 0, s>>>((const V*)in, (V*)out, d_ins, d_outs, p);
+  if (total + 4 * blocks * 256 < (int64_t(1) << 31))
+    rowcopy_kernel<V, uint32_t><<<dim3((unsigned)blocks, (unsigned)ntiles), 256, 0, s>>>((const V*)in, (V*)out, d_ins, d_outs, p);
+  else
+    rowcopy_kernel<V, int64_t><<<dim3((unsigned)blocks, (unsigned)ntiles), 256, 0, s>>>((const V*)in, (V*)out, d_ins, d_outs, p);
   ctx->launches++;
   TADEV_CHECK_CUDA(cudaGetLastError());
   return TADEV_OK;
