@@ -226,14 +226,27 @@ typedef struct {
   int32_t accumulate;       /* 0: C = alpha*A*B ; 1: C += */
   int32_t depth;            /* SUMMA pipeline depth (0 = reference default, :1925-1977) */
   int32_t steps_per_launch; /* K steps fused into one grouped-GEMM launch (0 = auto) */
+  /* TADEV_SUMMA_*_ON_HOST: the tile table of that array holds PINNED HOST pointers (TiledArray's
+   * arrays live in host memory; the reference GPU path migrates tiles through unified memory,
+   * device/um_storage.h:52-79). Host operands are streamed to the device panel by panel on a
+   * copy stream, overlapped with the GEMM of the previous window; a host result is produced in
+   * row blocks, each copied back while the next block computes. Also the out-of-core path. */
+  int32_t flags;
+  int32_t row_blocks;       /* result row blocks when the result is on the host (0 = auto) */
   int32_t reserved;
 } tadev_summa_plan;
+#define TADEV_SUMMA_A_ON_HOST 1
+#define TADEV_SUMMA_B_ON_HOST 2
+#define TADEV_SUMMA_C_ON_HOST 4
 
 typedef struct {
   int64_t nsteps, nsteps_skipped, npairs, nlaunches;
   double flops;       /* 2*m*n*k summed over executed pairs on this rank */
   int64_t bcast_bytes; /* bytes this rank sent or received in panel broadcasts */
   float device_ms;    /* CUDA-event time of the whole contraction on this rank */
+  int32_t row_blocks; /* result row blocks used */
+  int64_t h2d_bytes;  /* host->device bytes moved inside the call (host-resident operands) */
+  int64_t d2h_bytes;  /* device->host bytes moved inside the call (host-resident result) */
 } tadev_summa_stats;
 
 int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_stats* stats);

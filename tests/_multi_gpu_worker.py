@@ -2,7 +2,7 @@
 
 Contracts C[m,n] = A[m,k] * B[k,n] with the SUMMA driver over NCCL and checks every local result
 tile against the oracle (inputs are regenerated on the host from the counter RNG).
-usage: _multi_gpu_worker.py <Mt> <Kt> <Nt> <tile> <density> <steps_per_launch>
+usage: _multi_gpu_worker.py <Mt> <Kt> <Nt> <tile> <density> <steps_per_launch> [device|host]
 """
 import os
 import sys
@@ -24,6 +24,8 @@ from tiledarray_b200.tiledarray import ContEngine, DistArray, SparseShape, Tiled
 def main():
     Mt, Kt, Nt, tile = (int(x) for x in sys.argv[1:5])
     density = float(sys.argv[5])
+    ContEngine.steps_per_launch = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+    memory = sys.argv[7] if len(sys.argv) > 7 else "device"
     rank, size, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -39,10 +41,10 @@ def main():
         nA = np.where(rng.random((Mt, Kt)) < density, float(tile), 0.0).astype(np.float32)
         nB = np.where(rng.random((Kt, Nt)) < density, float(tile), 0.0).astype(np.float32)
         shA, shB = SparseShape(world, nA, trA), SparseShape(world, nB, trB)
-    a, b = summa_arrays(world, trA, trB, shA, shB)
+    a, b = summa_arrays(world, trA, trB, shA, shB, memory)
     a.fill_random(101)
     b.fill_random(202)
-    c = DistArray(world, trC)
+    c = DistArray(world, trC, memory=memory)
     c["m,n"] = a["m,k"] * b["k,n"]
     st = ContEngine.last_stats
     # oracle check of every local result tile

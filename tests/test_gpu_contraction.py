@@ -183,3 +183,48 @@ def test_cont_errors(world):
         c["m,n"] = a["m,k,z"] * b["k,n"]
     for x in (a, b, c):
         x.release()
+
+
+@pytest.mark.parametrize("where", [("host", "host", "host"), ("host", "device", "device"), ("device", "host", "host"),
+                                   ("device", "device", "host")])
+@pytest.mark.parametrize("sparse", [False, True])
+def test_cont_host_resident_arrays(world, where, sparse):
+    """Host-resident (pinned) operands/result: the SUMMA driver streams operand panels to the
+    device window by window and returns the result in row blocks (tadev.h TADEV_SUMMA_*_ON_HOST);
+    small windows / several row blocks / ragged tiles exercise every pipeline edge. Exact (int)."""
+    rng = np.random.default_rng(17 + sparse)
+    dm, dk, dn = TiledRange1(0, 4, 10, 16, 18, 30, 32), TiledRange1(0, 6, 8, 20, 22, 30), TiledRange1(0, 2, 12, 20, 24)
+    trL, trR, trC = _tr(dm, dk), _tr(dk, dn), _tr(dm, dn)
+
+    def make(tr, mem):
+        full = KA.int_tile(rng, tr.elements_shape)
+        sh = None
+        if sparse:
+            norms = np.zeros(tr.tiles_shape, dtype=np.float32)
+            for o in range(tr.ntiles):
+                idx = tr.tile_index(o)
+                if rng.random() < 0.6:
+                    norms[idx] = np.float32(np.linalg.norm(full[tr.tile_slices(idx)]))
+                else:
+                    full[tr.tile_slices(idx)] = 0.0
+            sh = SparseShape(world, norms, tr)
+        return DistArray(world, tr, sh, memory=mem).init_from_numpy(full), full
+
+    a, A = make(trL, where[0])
+    b, B = make(trR, where[1])
+    c = DistArray(world, trC, memory=where[2])
+    old = (ContEngine.steps_per_launch, ContEngine.row_blocks)
+    try:
+        for spl, rb in ((0, 0), (2, 3), (1, 6)):
+            ContEngine.steps_per_launch, ContEngine.row_blocks = spl, rb
+            c["m,n"] = a["m,k"] * b["k,n"]
+            assert np.array_equal(c.to_numpy(), A @ B), (spl, rb)
+            st = ContEngine.last_stats
+            if where[2] == "host":
+                assert st.d2h_bytes == sum(t.nbytes for t in c.tiles.values())
+            if where[0] == "host" and not sparse and where[2] != "host":
+                assert st.h2d_bytes >= A.nbytes  # every A tile uploaded exactly once
+    finally:
+        ContEngine.steps_per_launch, ContEngine.row_blocks = old
+    for x in (a, b, c):
+        x.release()

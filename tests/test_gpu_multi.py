@@ -45,3 +45,14 @@ def test_summa_nccl(case):
     nproc = 8 if n >= 8 else (4 if n >= 4 else 2)
     res = _run(nproc, list(case) + [0])
     assert "ok=True" in res, res
+
+
+@pytest.mark.parametrize("case", [(6, 5, 6, 128, 1.0), (8, 8, 8, 64, 0.4)])
+def test_summa_nccl_host_resident(case):
+    """Same, with operands and result in pinned host memory (streamed panels + row blocks)."""
+    n = _ngpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nproc = 8 if n >= 8 else (4 if n >= 4 else 2)
+    res = _run(nproc, list(case) + [2, "host"])
+    assert "ok=True" in res, res

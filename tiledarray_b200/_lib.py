@@ -52,12 +52,17 @@ class SummaPlanC(C.Structure):
                 ("a_norms", C.POINTER(C.c_float)), ("b_norms", C.POINTER(C.c_float)), ("c_norms", C.POINTER(C.c_float)),
                 ("threshold", C.c_float),
                 ("a_tiles", C.POINTER(C.c_void_p)), ("b_tiles", C.POINTER(C.c_void_p)), ("c_tiles", C.POINTER(C.c_void_p)),
-                ("accumulate", C.c_int32), ("depth", C.c_int32), ("steps_per_launch", C.c_int32), ("reserved", C.c_int32)]
+                ("accumulate", C.c_int32), ("depth", C.c_int32), ("steps_per_launch", C.c_int32),
+                ("flags", C.c_int32), ("row_blocks", C.c_int32), ("reserved", C.c_int32)]
+
+
+SUMMA_A_ON_HOST, SUMMA_B_ON_HOST, SUMMA_C_ON_HOST = 1, 2, 4
 
 
 class SummaStatsC(C.Structure):
     _fields_ = [("nsteps", C.c_int64), ("nsteps_skipped", C.c_int64), ("npairs", C.c_int64), ("nlaunches", C.c_int64),
-                ("flops", C.c_double), ("bcast_bytes", C.c_int64), ("device_ms", C.c_float)]
+                ("flops", C.c_double), ("bcast_bytes", C.c_int64), ("device_ms", C.c_float), ("row_blocks", C.c_int32),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 # every exported symbol of include/tadev.h with its prototype (restype, argtypes)

@@ -82,17 +82,30 @@ extern "C" int tadev_bcast_panel(tadev_ctx* ctx, tadev_stream s, int which, int 
 
 namespace {
 
-struct PanelTile { int idx; size_t off; size_t elems; };  // tile row/col index, offset (doubles) in panel
-
 inline size_t pad2(size_t n) { return (n + 1) & ~size_t(1); }  // keep every tile 16-byte aligned
 
+struct Bcast { void* ptr; size_t bytes; int root; };
+
+// A SUMMA step restricted to one row block of the result.
+struct BlockStep {
+  const SummaStep* st;
+  std::vector<int> a_rows;  // st->a_rows ∩ block rows
+  bool bcast_a, bcast_b, compute;
+  size_t a_elems, b_elems;  // padded panel sizes (doubles)
+};
+
 struct Window {
-  std::vector<int> steps;  // indices into schedule.steps
-  size_t bytes = 0;        // panel-buffer bytes needed
+  std::vector<int> steps;  // indices into the block's BlockStep list
+  size_t bytes = 0;        // ring bytes needed
 };
 
 }  // namespace
 
+// -----------------------------------------------------------------------------------------------
+// The driver. Loops: row blocks of the result (1 unless the result lives in host memory) ->
+// windows of K steps -> [H2D staging of host-resident panels | NCCL panel broadcasts] overlapped
+// with ONE grouped GEMM launch per window; finished result blocks are copied to the host while
+// the next block computes. See the file header for the reference mapping.
 extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_stats* stats) {
   TADEV_REQUIRE(ctx && plan, "tadev_summa_f64: null");
   const tadev_summa_plan& P = *plan;
@@ -106,16 +119,47 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   const bool multi = (Pr * Pc > 1);
   TADEV_REQUIRE(!multi || (ctx->row_comm && ctx->col_comm), "tadev_summa_f64: communicators not initialised");
   const int Mt = P.Mt, Nt = P.Nt, Kt = P.Kt;
+  const bool a_host = (P.flags & TADEV_SUMMA_A_ON_HOST) != 0, b_host = (P.flags & TADEV_SUMMA_B_ON_HOST) != 0,
+             c_host = (P.flags & TADEV_SUMMA_C_ON_HOST) != 0;
   TADEV_CHECK_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t s0 = ctx->streams[0];
-  cudaStream_t sc = ctx->comm_stream[0];
+  cudaStream_t s0 = ctx->streams[0];                       // compute
+  cudaStream_t sd = ctx->streams[ctx->streams.size() > 1 ? 1 : 0];  // result download
+  cudaStream_t sc = ctx->comm_stream[0];                   // NCCL panel broadcasts
+  cudaStream_t sh = ctx->comm_stream[1];                   // host -> device panel staging
 
   SummaSchedule S = make_summa_schedule(Pr, Pc, r, c, Mt, Nt, Kt, P.a_norms, P.b_norms, P.c_norms, P.threshold);
 
-  // ---- windows of steps (one grouped-GEMM launch each)
+  // ---- row blocks (deterministic from global quantities: every rank must agree on the count
+  //      because B panels are re-broadcast per block unless they are cached)
+  std::vector<int> my_rows;
+  for (int i = r; i < Mt; i += Pr) my_rows.push_back(i);
+  int nb = 1;
+  if (c_host) {
+    const int max_rows = (Mt + Pr - 1) / Pr;
+    double m_sum = 0, n_sum = 0;
+    for (int i = 0; i < Mt; ++i) m_sum += (double)P.m_ext[i];
+    for (int j = 0; j < Nt; ++j) n_sum += (double)P.n_ext[j];
+    const double c_bytes = (m_sum / Pr) * (n_sum / Pc) * 8.0;
+    nb = P.row_blocks > 0 ? P.row_blocks : (int)std::ceil(c_bytes / (2.0 * 1073741824.0));
+    nb = std::max(nb, std::min(4, max_rows));
+    nb = std::max(1, std::min(nb, max_rows));
+  }
+  // B staged through the device (received by broadcast or uploaded from the host) is kept for all
+  // row blocks when it fits the cache budget; the dense upper bound is the same on every rank.
+  const bool b_staged = b_host || (multi && Pr > 1);
+  bool b_cache = false;
+  if (nb > 1 && b_staged) {
+    double k_sum = 0, n_max = 0;
+    for (int k = 0; k < Kt; ++k) k_sum += (double)P.k_ext[k];
+    for (int cc = 0; cc < Pc; ++cc) { double t = 0; for (int j = cc; j < Nt; j += Pc) t += (double)P.n_ext[j]; n_max = std::max(n_max, t); }
+    double limit = 48.0 * 1073741824.0;
+    if (const char* e = getenv("TADEV_B_CACHE_GB")) limit = atof(e) * 1073741824.0;
+    b_cache = k_sum * n_max * 8.0 <= limit;
+  }
+
   int W = P.steps_per_launch;
   if (W <= 0) {
-    if (!multi) W = std::max(1, Kt);
+    if (!multi && !a_host && !b_host) W = std::max(1, Kt);
     else {
       double avgk = 0;
       for (int k = 0; k < Kt; ++k) avgk += (double)P.k_ext[k];
@@ -124,246 +168,381 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     }
   }
   const size_t kMaxWindowBytes = size_t(3) << 30;
-  auto a_panel_elems = [&](const SummaStep& st) { size_t e = 0; for (int i : st.a_rows) e += pad2((size_t)P.m_ext[i] * P.k_ext[st.k]); return e; };
-  auto b_panel_elems = [&](const SummaStep& st) { size_t e = 0; for (int j : st.b_cols) e += pad2((size_t)P.k_ext[st.k] * P.n_ext[j]); return e; };
-  std::vector<Window> windows;
-  {
-    Window cur;
-    int ncomp = 0;
-    for (int si = 0; si < (int)S.steps.size(); ++si) {
-      const SummaStep& st = S.steps[si];
-      size_t need = 0;
-      if (st.bcast_a) need += a_panel_elems(st) * 8;
-      if (st.bcast_b) need += b_panel_elems(st) * 8;
-      if (!cur.steps.empty() && (ncomp >= W || cur.bytes + need > kMaxWindowBytes)) {
-        windows.push_back(std::move(cur)); cur = Window(); ncomp = 0;
-      }
-      cur.steps.push_back(si); cur.bytes += need;
-      if (st.compute) ++ncomp;
-    }
-    if (!cur.steps.empty()) windows.push_back(std::move(cur));
-  }
-  size_t max_bytes = 0;
-  for (auto& w : windows) max_bytes = std::max(max_bytes, w.bytes);
   const int D = std::max(2, P.depth > 0 ? P.depth : 2);
 
+  // ---- per-block step views and windows
+  auto tile_a_elems = [&](int i, int k) { return (size_t)P.m_ext[i] * (size_t)P.k_ext[k]; };
+  auto tile_b_elems = [&](int k, int j) { return (size_t)P.k_ext[k] * (size_t)P.n_ext[j]; };
+  std::vector<std::vector<BlockStep>> bsteps(nb);
+  std::vector<std::vector<Window>> bwins(nb);
+  std::vector<std::pair<int, int>> brange(nb);  // [first, last) positions in my_rows
+  size_t max_bytes = 0, b_cache_elems = 0;
+  std::vector<size_t> b_cache_off(S.steps.size(), 0);
+  for (size_t si = 0; si < S.steps.size(); ++si) {
+    size_t e = 0;
+    for (int j : S.steps[si].b_cols) e += pad2(tile_b_elems(S.steps[si].k, j));
+    b_cache_off[si] = b_cache_elems;
+    if (b_cache && (S.steps[si].bcast_b || b_host)) b_cache_elems += e;
+  }
+  for (int b = 0; b < nb; ++b) {
+    const int L = (int)my_rows.size();
+    const int lo = (int)((int64_t)L * b / nb), hi = (int)((int64_t)L * (b + 1) / nb);
+    brange[b] = {lo, hi};
+    const int row_lo = lo < L ? my_rows[lo] : Mt, row_hi = hi < L ? my_rows[hi] : Mt;  // global row bounds
+    for (size_t si = 0; si < S.steps.size(); ++si) {
+      const SummaStep& st = S.steps[si];
+      BlockStep bs;
+      bs.st = &st;
+      for (int i : st.a_rows) if (i >= row_lo && i < row_hi) bs.a_rows.push_back(i);
+      bs.a_elems = 0;
+      for (int i : bs.a_rows) bs.a_elems += pad2(tile_a_elems(i, st.k));
+      bs.b_elems = 0;
+      for (int j : st.b_cols) bs.b_elems += pad2(tile_b_elems(st.k, j));
+      // a panel travels iff the (block-restricted) panel is non-empty and some rank can use it;
+      // every member of the row group shares the same rows, so the decision is group-consistent
+      bs.bcast_a = st.bcast_a && !bs.a_rows.empty();
+      bs.bcast_b = st.bcast_b && !(b_cache && b > 0);
+      bs.compute = !bs.a_rows.empty() && !st.b_cols.empty();
+      if (bs.compute || bs.bcast_a || bs.bcast_b) bsteps[b].push_back(std::move(bs));
+    }
+    Window cur;
+    int ncomp = 0;
+    for (int x = 0; x < (int)bsteps[b].size(); ++x) {
+      const BlockStep& bs = bsteps[b][x];
+      size_t need = 0;
+      if (bs.bcast_a || (a_host && bs.compute)) need += bs.a_elems * 8;
+      const bool b_to_cache = b_cache && (bs.st->bcast_b || b_host);
+      if (!b_to_cache && (bs.bcast_b || (b_host && bs.compute))) need += bs.b_elems * 8;
+      // the very first window is a single step so that the pipeline fills quickly
+      const int wcap = (b == 0 && bwins[b].empty()) ? 1 : W;
+      if (!cur.steps.empty() && (ncomp >= wcap || cur.bytes + need > kMaxWindowBytes)) {
+        bwins[b].push_back(std::move(cur)); cur = Window(); ncomp = 0;
+      }
+      cur.steps.push_back(x); cur.bytes += need;
+      if (bs.compute) ++ncomp;
+    }
+    if (!cur.steps.empty()) bwins[b].push_back(std::move(cur));
+    for (auto& w : bwins[b]) max_bytes = std::max(max_bytes, w.bytes);
+  }
+  if (!multi && !a_host && !b_host) {  // P == 1, device-resident: undo the short first window
+    // (no staging at all, so one launch for everything is best)
+    for (int b = 0; b < nb; ++b) {
+      Window all;
+      for (int x = 0; x < (int)bsteps[b].size(); ++x) all.steps.push_back(x);
+      bwins[b].clear();
+      if (!all.steps.empty()) {
+        if (P.steps_per_launch > 0) {
+          Window cur; int ncomp = 0;
+          for (int x : all.steps) {
+            if (!cur.steps.empty() && ncomp >= P.steps_per_launch) { bwins[b].push_back(std::move(cur)); cur = Window(); ncomp = 0; }
+            cur.steps.push_back(x);
+            if (bsteps[b][x].compute) ++ncomp;
+          }
+          if (!cur.steps.empty()) bwins[b].push_back(std::move(cur));
+        } else bwins[b].push_back(std::move(all));
+      }
+    }
+    max_bytes = 0;
+  }
+
   // ---- resources
-  cudaEvent_t ev_start, ev_end, ev_comm_done;
+  cudaEvent_t ev_start, ev_end, ev_aux;
   TADEV_CHECK_CUDA(cudaEventCreate(&ev_start));
   TADEV_CHECK_CUDA(cudaEventCreate(&ev_end));
-  TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&ev_comm_done, cudaEventDisableTiming));
+  TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&ev_aux, cudaEventDisableTiming));
+  const bool need_ring = max_bytes > 0;
   std::vector<double*> ring(D, nullptr);
-  std::vector<cudaEvent_t> panel_ready(D), buf_free(D);
+  std::vector<cudaEvent_t> panel_ready(D), buf_free(D), h2d_done(D);
   std::vector<char> buf_used(D, 0);
-  const bool need_ring = multi && max_bytes > 0;
-  if (need_ring) {
-    for (int d = 0; d < D; ++d) {
-      int rc = tadev_alloc(ctx, max_bytes, (void**)&ring[d], s0);
-      if (rc) return rc;
-      TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&panel_ready[d], cudaEventDisableTiming));
-      TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&buf_free[d], cudaEventDisableTiming));
+  for (int d = 0; d < D; ++d) {
+    if (need_ring) { int rc = tadev_alloc(ctx, max_bytes, (void**)&ring[d], s0); if (rc) return rc; }
+    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&panel_ready[d], cudaEventDisableTiming));
+    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&buf_free[d], cudaEventDisableTiming));
+    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&h2d_done[d], cudaEventDisableTiming));
+  }
+  double* bcache = nullptr;
+  if (b_cache && b_cache_elems) { int rc = tadev_alloc(ctx, b_cache_elems * 8, (void**)&bcache, s0); if (rc) return rc; }
+  // result blocks staged on the device when the result lives in host memory (double buffered)
+  std::vector<size_t> cblock_elems(nb, 0);
+  auto c_local = [&](int i, int j) {
+    return (j % Pc == c) && (!P.c_norms || P.c_norms[(size_t)i * Nt + j] >= P.threshold) && P.c_tiles[(size_t)i * Nt + j] != nullptr;
+  };
+  size_t cmax = 0;
+  if (c_host) {
+    for (int b = 0; b < nb; ++b) {
+      for (int x = brange[b].first; x < brange[b].second; ++x)
+        for (int j = c; j < Nt; j += Pc)
+          if (c_local(my_rows[x], j)) cblock_elems[b] += pad2((size_t)P.m_ext[my_rows[x]] * P.n_ext[j]);
+      cmax = std::max(cmax, cblock_elems[b]);
     }
   }
+  double* carena[2] = {nullptr, nullptr};
+  cudaEvent_t c_done[2], d2h_done[2];
+  bool c_used[2] = {false, false};
+  for (int x = 0; x < 2; ++x) {
+    if (c_host && cmax) { int rc = tadev_alloc(ctx, cmax * 8, (void**)&carena[x], s0); if (rc) return rc; }
+    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&c_done[x], cudaEventDisableTiming));
+    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&d2h_done[x], cudaEventDisableTiming));
+  }
   TADEV_CHECK_CUDA(cudaEventRecord(ev_start, s0));
-  if (need_ring) TADEV_CHECK_CUDA(cudaStreamWaitEvent(sc, ev_start, 0));
+  TADEV_CHECK_CUDA(cudaStreamWaitEvent(sc, ev_start, 0));
+  TADEV_CHECK_CUDA(cudaStreamWaitEvent(sh, ev_start, 0));
+  TADEV_CHECK_CUDA(cudaStreamWaitEvent(sd, ev_start, 0));
 
   std::vector<char> touched((size_t)Mt * Nt, 0);
-  int64_t npairs = 0, nlaunches = 0, bcast_bytes = 0;
+  int64_t npairs = 0, nlaunches = 0, bcast_bytes = 0, h2d_bytes = 0, d2h_bytes = 0;
   double flops = 0.0;
-
   struct Contribution { int64_t key; const double* A; const double* B; int k; };
   std::vector<Contribution> contrib;
   std::vector<tadev_gemm_group> groups;
   std::vector<tadev_gemm_task> tasks;
+  std::vector<double*> c_dev((size_t)Mt * Nt, nullptr);  // device address of each local result tile
+  int64_t wcount = 0;                                     // global window counter -> ring slot
+  std::vector<char> b_cached(S.steps.size(), 0);
 
-  for (int wi = 0; wi < (int)windows.size(); ++wi) {
-    const Window& win = windows[wi];
-    const int d = wi % D;
-    double* buf = need_ring ? ring[d] : nullptr;
-    size_t cursor = 0;  // doubles
-    bool any_comm = false;
-    // per-step resolved tile pointers for the GEMM tasks
-    std::vector<std::vector<const double*>> a_ptrs(win.steps.size()), b_ptrs(win.steps.size());
-
-    if (need_ring && win.bytes > 0 && buf_used[d]) TADEV_CHECK_CUDA(cudaStreamWaitEvent(sc, buf_free[d], 0));
-
-    struct Bcast { void* ptr; size_t bytes; int root; };
-    std::vector<Bcast> row_bcasts, col_bcasts;
-
-    for (size_t wsi = 0; wsi < win.steps.size(); ++wsi) {
-      const SummaStep& st = S.steps[win.steps[wsi]];
-      const int k = st.k;
-      // ---- A panel (travels along my grid row)
-      {
-        auto& ptrs = a_ptrs[wsi];
-        ptrs.resize(st.a_rows.size(), nullptr);
-        const int root = k % Pc;
-        if (st.bcast_a) {
-          const size_t elems = a_panel_elems(st);
-          double* panel = buf + cursor;
-          bool inplace = false;
-          if (c == root) {
-            // owner: tiles adjacent in panel order can be sent from where they live
-            inplace = true;
-            const double* first = P.a_tiles[(size_t)st.a_rows[0] * Kt + k];
-            size_t off = 0;
-            for (size_t n = 0; n < st.a_rows.size(); ++n) {
-              const double* tp = P.a_tiles[(size_t)st.a_rows[n] * Kt + k];
-              TADEV_REQUIRE(tp, "tadev_summa_f64: A tile (%d,%d) is owned by this rank but has no data", st.a_rows[n], k);
-              if (tp != first + off || (reinterpret_cast<uintptr_t>(tp) & 15)) inplace = false;
-              off += pad2((size_t)P.m_ext[st.a_rows[n]] * P.k_ext[k]);
-            }
-            if (inplace) panel = const_cast<double*>(first);
-            else {
-              size_t o = 0;
-              for (size_t n = 0; n < st.a_rows.size(); ++n) {
-                const size_t e = (size_t)P.m_ext[st.a_rows[n]] * P.k_ext[k];
-                TADEV_CHECK_CUDA(cudaMemcpyAsync(panel + o, P.a_tiles[(size_t)st.a_rows[n] * Kt + k], e * 8,
-                                                 cudaMemcpyDeviceToDevice, sc));
-                o += pad2(e);
-              }
-            }
-          }
-          if (!inplace) cursor += elems;
+  // Stage one panel: returns device pointers of its tiles. `mine` = I own the source tiles.
+  // host-resident sources are uploaded (sh), device-resident ones are used in place when they need
+  // no transport, broadcast in place when contiguous, or packed (sc).
+  auto stage_panel = [&](bool on_host, bool needs_bcast, bool mine, const std::vector<const double*>& src,
+                         const std::vector<size_t>& elems, double* dest, bool* used_dest, bool* did_h2d,
+                         std::vector<const double*>& out) -> int {
+    out.assign(src.size(), nullptr);
+    *used_dest = false;
+    if (!needs_bcast && !on_host) { for (size_t n = 0; n < src.size(); ++n) out[n] = src[n]; return TADEV_OK; }
+    double* panel = dest;
+    bool inplace = false;
+    if (mine) {
+      if (on_host) {
+        size_t o = 0;
+        for (size_t n = 0; n < src.size(); ++n) {
+          TADEV_CHECK_CUDA(cudaMemcpyAsync(panel + o, src[n], elems[n] * 8, cudaMemcpyHostToDevice, sh));
+          h2d_bytes += (int64_t)elems[n] * 8;
+          o += pad2(elems[n]);
+        }
+        *did_h2d = true;
+      } else {
+        inplace = true;
+        size_t off = 0;
+        for (size_t n = 0; n < src.size(); ++n) {
+          if (src[n] != src[0] + off || (reinterpret_cast<uintptr_t>(src[n]) & 15)) inplace = false;
+          off += pad2(elems[n]);
+        }
+        if (inplace) panel = const_cast<double*>(src[0]);
+        else {
           size_t o = 0;
-          for (size_t n = 0; n < st.a_rows.size(); ++n) {
-            ptrs[n] = panel + o;
-            o += pad2((size_t)P.m_ext[st.a_rows[n]] * P.k_ext[k]);
-          }
-          row_bcasts.push_back({panel, elems * 8, root});
-          bcast_bytes += (int64_t)elems * 8;
-          any_comm = true;
-        } else if (st.compute) {
-          for (size_t n = 0; n < st.a_rows.size(); ++n) {
-            ptrs[n] = P.a_tiles[(size_t)st.a_rows[n] * Kt + k];
-            TADEV_REQUIRE(ptrs[n], "tadev_summa_f64: A tile (%d,%d) has no data on this rank", st.a_rows[n], k);
+          for (size_t n = 0; n < src.size(); ++n) {
+            TADEV_CHECK_CUDA(cudaMemcpyAsync(panel + o, src[n], elems[n] * 8, cudaMemcpyDeviceToDevice, sc));
+            o += pad2(elems[n]);
           }
         }
       }
-      // ---- B panel (travels along my grid column)
-      {
-        auto& ptrs = b_ptrs[wsi];
-        ptrs.resize(st.b_cols.size(), nullptr);
-        const int root = k % Pr;
-        if (st.bcast_b) {
-          const size_t elems = b_panel_elems(st);
-          double* panel = buf + cursor;
-          bool inplace = false;
-          if (r == root) {
-            inplace = true;
-            const double* first = P.b_tiles[(size_t)k * Nt + st.b_cols[0]];
-            size_t off = 0;
-            for (size_t n = 0; n < st.b_cols.size(); ++n) {
-              const double* tp = P.b_tiles[(size_t)k * Nt + st.b_cols[n]];
-              TADEV_REQUIRE(tp, "tadev_summa_f64: B tile (%d,%d) is owned by this rank but has no data", k, st.b_cols[n]);
-              if (tp != first + off || (reinterpret_cast<uintptr_t>(tp) & 15)) inplace = false;
-              off += pad2((size_t)P.k_ext[k] * P.n_ext[st.b_cols[n]]);
+    }
+    *used_dest = !inplace;
+    size_t o = 0;
+    for (size_t n = 0; n < src.size(); ++n) { out[n] = panel + o; o += pad2(elems[n]); }
+    return TADEV_OK;
+  };
+
+  for (int b = 0; b < nb; ++b) {
+    // ---- device addresses of this block's result tiles
+    const int cslot = b & 1;
+    if (c_host) {
+      if (c_used[cslot]) TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, d2h_done[cslot], 0));  // block b-2 downloaded
+      size_t o = 0;
+      for (int x = brange[b].first; x < brange[b].second; ++x)
+        for (int j = c; j < Nt; j += Pc) {
+          const int i = my_rows[x];
+          if (!c_local(i, j)) continue;
+          c_dev[(size_t)i * Nt + j] = carena[cslot] + o;
+          const size_t e = (size_t)P.m_ext[i] * P.n_ext[j];
+          if (P.accumulate) {  // C += : bring the previous contents
+            TADEV_CHECK_CUDA(cudaMemcpyAsync(carena[cslot] + o, P.c_tiles[(size_t)i * Nt + j], e * 8, cudaMemcpyHostToDevice, s0));
+            h2d_bytes += (int64_t)e * 8;
+          }
+          o += pad2(e);
+        }
+    } else {
+      for (int x = brange[b].first; x < brange[b].second; ++x)
+        for (int j = c; j < Nt; j += Pc) c_dev[(size_t)my_rows[x] * Nt + j] = P.c_tiles[(size_t)my_rows[x] * Nt + j];
+    }
+
+    for (int wi = 0; wi < (int)bwins[b].size(); ++wi, ++wcount) {
+      const Window& win = bwins[b][wi];
+      const int d = (int)(wcount % D);
+      double* buf = ring[d];
+      size_t cursor = 0;
+      bool any_bcast = false, any_h2d = false, ring_touched = false;
+      std::vector<std::vector<const double*>> a_ptrs(win.steps.size()), b_ptrs(win.steps.size());
+      std::vector<Bcast> row_bcasts, col_bcasts;
+      if (need_ring && win.bytes > 0 && buf_used[d]) {  // the GEMM that last read this slot is done
+        TADEV_CHECK_CUDA(cudaStreamWaitEvent(sc, buf_free[d], 0));
+        TADEV_CHECK_CUDA(cudaStreamWaitEvent(sh, buf_free[d], 0));
+      }
+      for (size_t wsi = 0; wsi < win.steps.size(); ++wsi) {
+        const BlockStep& bs = bsteps[b][win.steps[wsi]];
+        const SummaStep& st = *bs.st;
+        const int k = st.k;
+        const size_t si = (size_t)(bs.st - &S.steps[0]);
+        std::vector<const double*> src;
+        std::vector<size_t> el;
+        // ---- A panel (travels along my grid row; root column k % Pc)
+        if (bs.bcast_a || bs.compute) {
+          const bool mine = (c == k % Pc);
+          src.clear(); el.clear();
+          for (int i : bs.a_rows) {
+            const double* tp = P.a_tiles[(size_t)i * Kt + k];
+            TADEV_REQUIRE(!mine || tp, "tadev_summa_f64: A tile (%d,%d) is owned by this rank but has no data", i, k);
+            src.push_back(tp); el.push_back(tile_a_elems(i, k));
+          }
+          bool used = false;
+          int rc = stage_panel(a_host, bs.bcast_a, mine, src, el, buf ? buf + cursor : nullptr, &used, &any_h2d, a_ptrs[wsi]);
+          if (rc) return rc;
+          if (used) { cursor += bs.a_elems; ring_touched = true; }
+          if (bs.bcast_a) {
+            row_bcasts.push_back({const_cast<double*>(a_ptrs[wsi][0]), bs.a_elems * 8, k % Pc});
+            bcast_bytes += (int64_t)bs.a_elems * 8;
+            any_bcast = true;
+          }
+        }
+        // ---- B panel (travels along my grid column; root row k % Pr); cached across row blocks
+        if (bs.bcast_b || bs.compute) {
+          const bool to_cache = b_cache && (st.bcast_b || b_host);
+          if (to_cache && b_cached[si]) {
+            size_t o = 0;
+            b_ptrs[wsi].clear();
+            for (int j : st.b_cols) { b_ptrs[wsi].push_back(bcache + b_cache_off[si] + o); o += pad2(tile_b_elems(k, j)); }
+          } else {
+            const bool mine = (r == k % Pr);
+            src.clear(); el.clear();
+            for (int j : st.b_cols) {
+              const double* tp = P.b_tiles[(size_t)k * Nt + j];
+              TADEV_REQUIRE(!mine || tp, "tadev_summa_f64: B tile (%d,%d) is owned by this rank but has no data", k, j);
+              src.push_back(tp); el.push_back(tile_b_elems(k, j));
             }
-            if (inplace) panel = const_cast<double*>(first);
-            else {
-              size_t o = 0;
-              for (size_t n = 0; n < st.b_cols.size(); ++n) {
-                const size_t e = (size_t)P.k_ext[k] * P.n_ext[st.b_cols[n]];
-                TADEV_CHECK_CUDA(cudaMemcpyAsync(panel + o, P.b_tiles[(size_t)k * Nt + st.b_cols[n]], e * 8,
-                                                 cudaMemcpyDeviceToDevice, sc));
-                o += pad2(e);
+            double* dest = to_cache ? bcache + b_cache_off[si] : (buf ? buf + cursor : nullptr);
+            bool used = false;
+            int rc = stage_panel(b_host, bs.bcast_b, mine, src, el, dest, &used, &any_h2d, b_ptrs[wsi]);
+            if (rc) return rc;
+            if (used && !to_cache) { cursor += bs.b_elems; ring_touched = true; }
+            if (to_cache) {
+              // an in-place broadcast source lives outside the cache: mirror it so later blocks find it
+              if (!used && !st.b_cols.empty()) {
+                TADEV_CHECK_CUDA(cudaMemcpyAsync(dest, b_ptrs[wsi][0], bs.b_elems * 8, cudaMemcpyDeviceToDevice, sc));
               }
+              b_cached[si] = 1;
+            }
+            if (bs.bcast_b) {
+              col_bcasts.push_back({const_cast<double*>(b_ptrs[wsi][0]), bs.b_elems * 8, k % Pr});
+              bcast_bytes += (int64_t)bs.b_elems * 8;
+              any_bcast = true;
             }
           }
-          if (!inplace) cursor += elems;
-          size_t o = 0;
-          for (size_t n = 0; n < st.b_cols.size(); ++n) {
-            ptrs[n] = panel + o;
-            o += pad2((size_t)P.k_ext[k] * P.n_ext[st.b_cols[n]]);
-          }
-          col_bcasts.push_back({panel, elems * 8, root});
-          bcast_bytes += (int64_t)elems * 8;
-          any_comm = true;
-        } else if (st.compute) {
-          for (size_t n = 0; n < st.b_cols.size(); ++n) {
-            ptrs[n] = P.b_tiles[(size_t)k * Nt + st.b_cols[n]];
-            TADEV_REQUIRE(ptrs[n], "tadev_summa_f64: B tile (%d,%d) has no data on this rank", k, st.b_cols[n]);
-          }
         }
       }
-    }
-    if (any_comm) {
-      // same (comm, k) order on every rank of a group => no cross-communicator deadlock
-      if (!row_bcasts.empty()) {
-        TADEV_CHECK_NCCL(ncclGroupStart());
-        for (auto& bc : row_bcasts) TADEV_CHECK_NCCL(ncclBroadcast(bc.ptr, bc.ptr, bc.bytes, ncclChar, bc.root, ctx->row_comm, sc));
-        TADEV_CHECK_NCCL(ncclGroupEnd());
+      // ---- ordering: H2D (sh) -> broadcasts (sc) -> GEMM (s0)
+      if (any_h2d) {
+        TADEV_CHECK_CUDA(cudaEventRecord(h2d_done[d], sh));
+        TADEV_CHECK_CUDA(cudaStreamWaitEvent(any_bcast ? sc : s0, h2d_done[d], 0));
       }
-      if (!col_bcasts.empty()) {
-        TADEV_CHECK_NCCL(ncclGroupStart());
-        for (auto& bc : col_bcasts) TADEV_CHECK_NCCL(ncclBroadcast(bc.ptr, bc.ptr, bc.bytes, ncclChar, bc.root, ctx->col_comm, sc));
-        TADEV_CHECK_NCCL(ncclGroupEnd());
-      }
-      TADEV_CHECK_CUDA(cudaEventRecord(panel_ready[d], sc));
-      TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, panel_ready[d], 0));
-    }
-
-    // ---- grouped GEMM descriptors of this window: chain contributions per result tile
-    contrib.clear();
-    for (size_t wsi = 0; wsi < win.steps.size(); ++wsi) {
-      const SummaStep& st = S.steps[win.steps[wsi]];
-      if (!st.compute) continue;
-      // index of a global row/col inside this step's panel lists
-      size_t ai = 0;
-      for (int64_t pp = st.pair_begin; pp < st.pair_end; ++pp) {
-        const int i = S.pair_i[pp], j = S.pair_j[pp];
-        while (st.a_rows[ai] != i) ++ai;  // pairs are row-major: rows appear in a_rows order
-        const size_t bj = std::lower_bound(st.b_cols.begin(), st.b_cols.end(), j) - st.b_cols.begin();
-        contrib.push_back({(int64_t)i * Nt + j, a_ptrs[wsi][ai], b_ptrs[wsi][bj], (int)P.k_ext[st.k]});
-        flops += 2.0 * (double)P.m_ext[i] * (double)P.n_ext[j] * (double)P.k_ext[st.k];
-      }
-    }
-    npairs += (int64_t)contrib.size();
-    if (!contrib.empty()) {
-      std::stable_sort(contrib.begin(), contrib.end(), [](const Contribution& x, const Contribution& y) { return x.key < y.key; });
-      groups.clear(); tasks.clear();
-      for (size_t n = 0; n < contrib.size(); ++n) {
-        if (n == 0 || contrib[n].key != contrib[n - 1].key) {
-          const int i = (int)(contrib[n].key / Nt), j = (int)(contrib[n].key % Nt);
-          double* ct = P.c_tiles[contrib[n].key];
-          TADEV_REQUIRE(ct, "tadev_summa_f64: result tile (%d,%d) is non-zero and local but has no storage", i, j);
-          if (!groups.empty()) groups.back().task_end = (int32_t)tasks.size();
-          tadev_gemm_group G{ct, (int32_t)P.m_ext[i], (int32_t)P.n_ext[j], (int32_t)tasks.size(), 0,
-                             (P.accumulate || touched[contrib[n].key]) ? 1 : 0, 0};
-          touched[contrib[n].key] = 1;
-          groups.push_back(G);
+      if (any_bcast) {
+        // same (communicator, k) order on every rank of a group => no cross-communicator deadlock
+        if (!row_bcasts.empty()) {
+          TADEV_CHECK_NCCL(ncclGroupStart());
+          for (auto& bc : row_bcasts) TADEV_CHECK_NCCL(ncclBroadcast(bc.ptr, bc.ptr, bc.bytes, ncclChar, bc.root, ctx->row_comm, sc));
+          TADEV_CHECK_NCCL(ncclGroupEnd());
         }
-        tasks.push_back({contrib[n].A, contrib[n].B, contrib[n].k, 0});
+        if (!col_bcasts.empty()) {
+          TADEV_CHECK_NCCL(ncclGroupStart());
+          for (auto& bc : col_bcasts) TADEV_CHECK_NCCL(ncclBroadcast(bc.ptr, bc.ptr, bc.bytes, ncclChar, bc.root, ctx->col_comm, sc));
+          TADEV_CHECK_NCCL(ncclGroupEnd());
+        }
       }
-      groups.back().task_end = (int32_t)tasks.size();
-      int rc = tadev_gemm_grouped_f64(ctx, s0, P.opA, P.opB, P.alpha, groups.data(), (int)groups.size(), tasks.data(),
-                                      (int)tasks.size());
-      if (rc) return rc;
-      ++nlaunches;
-    }
-    if (need_ring && win.bytes > 0) {
-      TADEV_CHECK_CUDA(cudaEventRecord(buf_free[d], s0));
-      buf_used[d] = 1;
-    }
-  }
+      if (any_bcast || ring_touched) {  // D2D packs also run on sc
+        TADEV_CHECK_CUDA(cudaEventRecord(panel_ready[d], sc));
+        TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, panel_ready[d], 0));
+      }
 
-  // result tiles that are non-zero in the result shape but received no contribution
-  if (!P.accumulate) {
-    for (int i = r; i < Mt; i += Pr)
+      // ---- grouped GEMM descriptors of this window: chain contributions per result tile
+      contrib.clear();
+      for (size_t wsi = 0; wsi < win.steps.size(); ++wsi) {
+        const BlockStep& bs = bsteps[b][win.steps[wsi]];
+        if (!bs.compute) continue;
+        const SummaStep& st = *bs.st;
+        size_t ai = 0;
+        for (int64_t pp = st.pair_begin; pp < st.pair_end; ++pp) {
+          const int i = S.pair_i[pp], j = S.pair_j[pp];
+          if (bs.a_rows.empty() || i < bs.a_rows.front() || i > bs.a_rows.back()) continue;  // other row block
+          while (bs.a_rows[ai] != i) ++ai;  // pairs are row-major: rows appear in a_rows order
+          const size_t bj = std::lower_bound(st.b_cols.begin(), st.b_cols.end(), j) - st.b_cols.begin();
+          contrib.push_back({(int64_t)i * Nt + j, a_ptrs[wsi][ai], b_ptrs[wsi][bj], (int)P.k_ext[st.k]});
+          flops += 2.0 * (double)P.m_ext[i] * (double)P.n_ext[j] * (double)P.k_ext[st.k];
+        }
+      }
+      npairs += (int64_t)contrib.size();
+      if (!contrib.empty()) {
+        std::stable_sort(contrib.begin(), contrib.end(), [](const Contribution& x, const Contribution& y) { return x.key < y.key; });
+        groups.clear(); tasks.clear();
+        for (size_t n = 0; n < contrib.size(); ++n) {
+          if (n == 0 || contrib[n].key != contrib[n - 1].key) {
+            const int i = (int)(contrib[n].key / Nt), j = (int)(contrib[n].key % Nt);
+            double* ct = c_dev[contrib[n].key];
+            TADEV_REQUIRE(ct, "tadev_summa_f64: result tile (%d,%d) is non-zero and local but has no storage", i, j);
+            if (!groups.empty()) groups.back().task_end = (int32_t)tasks.size();
+            tadev_gemm_group G{ct, (int32_t)P.m_ext[i], (int32_t)P.n_ext[j], (int32_t)tasks.size(), 0,
+                               (P.accumulate || touched[contrib[n].key]) ? 1 : 0, 0};
+            touched[contrib[n].key] = 1;
+            groups.push_back(G);
+          }
+          tasks.push_back({contrib[n].A, contrib[n].B, contrib[n].k, 0});
+        }
+        groups.back().task_end = (int32_t)tasks.size();
+        int rc = tadev_gemm_grouped_f64(ctx, s0, P.opA, P.opB, P.alpha, groups.data(), (int)groups.size(), tasks.data(),
+                                        (int)tasks.size());
+        if (rc) return rc;
+        ++nlaunches;
+      }
+      if (need_ring && win.bytes > 0) {
+        TADEV_CHECK_CUDA(cudaEventRecord(buf_free[d], s0));
+        buf_used[d] = 1;
+      }
+    }
+
+    // ---- block epilogue: zero-fill untouched non-zero tiles, then hand the block to the host
+    for (int x = brange[b].first; x < brange[b].second; ++x)
       for (int j = c; j < Nt; j += Pc) {
-        const size_t key = (size_t)i * Nt + j;
-        const bool nz = !P.c_norms || P.c_norms[key] >= P.threshold;
-        if (nz && !touched[key] && P.c_tiles[key])
-          TADEV_CHECK_CUDA(cudaMemsetAsync(P.c_tiles[key], 0, (size_t)P.m_ext[i] * P.n_ext[j] * 8, s0));
+        const size_t key = (size_t)my_rows[x] * Nt + j;
+        if (!P.accumulate && c_dev[key] && !touched[key] && (!P.c_norms || P.c_norms[key] >= P.threshold))
+          TADEV_CHECK_CUDA(cudaMemsetAsync(c_dev[key], 0, (size_t)P.m_ext[my_rows[x]] * P.n_ext[j] * 8, s0));
       }
+    if (c_host && cblock_elems[b]) {
+      TADEV_CHECK_CUDA(cudaEventRecord(c_done[cslot], s0));
+      TADEV_CHECK_CUDA(cudaStreamWaitEvent(sd, c_done[cslot], 0));
+      for (int x = brange[b].first; x < brange[b].second; ++x)
+        for (int j = c; j < Nt; j += Pc) {
+          const size_t key = (size_t)my_rows[x] * Nt + j;
+          if (!c_local(my_rows[x], j)) continue;
+          const size_t e = (size_t)P.m_ext[my_rows[x]] * P.n_ext[j];
+          TADEV_CHECK_CUDA(cudaMemcpyAsync(P.c_tiles[key], c_dev[key], e * 8, cudaMemcpyDeviceToHost, sd));
+          d2h_bytes += (int64_t)e * 8;
+        }
+      TADEV_CHECK_CUDA(cudaEventRecord(d2h_done[cslot], sd));
+      c_used[cslot] = true;
+    }
   }
-  if (need_ring) {
-    TADEV_CHECK_CUDA(cudaEventRecord(ev_comm_done, sc));
-    TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, ev_comm_done, 0));
+
+  // ---- join all streams on s0, time, release
+  TADEV_CHECK_CUDA(cudaEventRecord(ev_aux, sc));
+  TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, ev_aux, 0));
+  TADEV_CHECK_CUDA(cudaEventRecord(ev_aux, sh));
+  TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, ev_aux, 0));
+  if (sd != s0) {
+    TADEV_CHECK_CUDA(cudaEventRecord(ev_aux, sd));
+    TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, ev_aux, 0));
   }
   TADEV_CHECK_CUDA(cudaEventRecord(ev_end, s0));
-  if (need_ring)
-    for (int d = 0; d < D; ++d) { int rc = tadev_free(ctx, ring[d], s0); if (rc) return rc; }
+  for (int d = 0; d < D; ++d) if (ring[d]) { int rc = tadev_free(ctx, ring[d], s0); if (rc) return rc; }
+  if (bcache) { int rc = tadev_free(ctx, bcache, s0); if (rc) return rc; }
+  for (int x = 0; x < 2; ++x) if (carena[x]) { int rc = tadev_free(ctx, carena[x], s0); if (rc) return rc; }
   TADEV_CHECK_CUDA(cudaEventSynchronize(ev_end));
   TADEV_CHECK_CUDA(cudaGetLastError());
   float ms = 0;
@@ -376,9 +555,12 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     stats->flops = flops;
     stats->bcast_bytes = bcast_bytes;
     stats->device_ms = ms;
+    stats->h2d_bytes = h2d_bytes;
+    stats->d2h_bytes = d2h_bytes;
+    stats->row_blocks = nb;
   }
-  cudaEventDestroy(ev_start); cudaEventDestroy(ev_end); cudaEventDestroy(ev_comm_done);
-  if (need_ring)
-    for (int d = 0; d < D; ++d) { cudaEventDestroy(panel_ready[d]); cudaEventDestroy(buf_free[d]); }
+  cudaEventDestroy(ev_start); cudaEventDestroy(ev_end); cudaEventDestroy(ev_aux);
+  for (int d = 0; d < D; ++d) { cudaEventDestroy(panel_ready[d]); cudaEventDestroy(buf_free[d]); cudaEventDestroy(h2d_done[d]); }
+  for (int x = 0; x < 2; ++x) { cudaEventDestroy(c_done[x]); cudaEventDestroy(d2h_done[x]); }
   return TADEV_OK;
 }

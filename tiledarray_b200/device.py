@@ -32,6 +32,34 @@ class DeviceBuffer:
         self.ptr = 0
 
 
+class HostBuffer:
+    """Pinned (page-locked) host memory from tadev_host_alloc: the home of host-resident tiles."""
+
+    __slots__ = ("ptr", "nbytes", "_owned")
+
+    def __init__(self, nbytes: int = 0, ptr: int = 0, owned: bool = True):
+        if owned:
+            p = C.c_void_p()
+            check(_lib.load().tadev_host_alloc(max(nbytes, 1), C.byref(p)))
+            ptr = p.value
+        self.ptr, self.nbytes, self._owned = ptr, nbytes, owned
+
+    def view(self, byte_offset: int, nbytes: int) -> "HostBuffer":
+        assert 0 <= byte_offset and byte_offset + nbytes <= self.nbytes
+        return HostBuffer(nbytes, self.ptr + byte_offset, owned=False)
+
+    def numpy(self, dtype, shape) -> np.ndarray:
+        n = int(np.prod(shape, dtype=np.int64))
+        assert n * np.dtype(dtype).itemsize <= self.nbytes
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def free(self) -> None:
+        if self._owned and self.ptr:
+            check(_lib.load().tadev_host_free(self.ptr))
+        self.ptr = 0
+
+
 class Device:
     def __init__(self, device: int = 0, pool_bytes: int = 0):
         self.lib = _lib.load()

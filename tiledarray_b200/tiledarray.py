@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import ContractionPlanC, ProcGridC, SummaPlanC, SummaStatsC, check
-from .device import Device, DeviceBuffer
+from .device import Device, DeviceBuffer, HostBuffer
 
 FLT_EPSILON = float(np.finfo(np.float32).eps)
 f32 = np.float32
@@ -294,8 +294,11 @@ class DistArray:
     """
 
     def __init__(self, world: World, trange: TiledRange, shape: Optional[SparseShape] = None,
-                 owner=None, arena_order: Optional[Sequence[int]] = None):
+                 owner=None, arena_order: Optional[Sequence[int]] = None, memory: str = "device"):
+        _ta_assert(memory in ("device", "host"), "DistArray: memory must be 'device' or 'host'")
         self.world, self.trange = world, trange
+        self.memory = memory  # "host": tiles live in pinned host memory (TiledArray's default home for
+        #                       arrays) and are streamed through the GPU by the SUMMA driver
         self.shape = shape if shape is not None else DenseShape()
         self._owner = owner or (lambda ordinal: 0)
         self.tiles: Dict[int, DeviceBuffer] = {}
@@ -324,7 +327,10 @@ class DistArray:
             ords.sort(key=lambda o: rank_of.get(o, o))
         sizes = [(self.tile_elems(o) + 1) & ~1 for o in ords]  # keep every tile 16-byte aligned
         total = sum(sizes)
-        self._arena = self.world.dev.alloc(max(total, 2) * 8)
+        if self.memory == "host":
+            self._arena = HostBuffer(max(total, 2) * 8)
+        else:
+            self._arena = self.world.dev.alloc(max(total, 2) * 8)
         off = 0
         for o, s in zip(ords, sizes):
             self.tiles[o] = self._arena.view(off * 8, self.tile_elems(o) * 8)
@@ -335,15 +341,29 @@ class DistArray:
         self._allocate()
         for o, buf in self.tiles.items():
             n = self.tile_elems(o)
-            self.world.dev.upload_into(buf, np.full(n, value, dtype=np.float64))
+            if self.memory == "host":
+                buf.numpy(np.float64, (n,))[:] = value
+            else:
+                self.world.dev.upload_into(buf, np.full(n, value, dtype=np.float64))
         return self
 
     def fill_random(self, seed: int) -> "DistArray":
         """uniform(-1,1) generated on the device; element value depends only on (seed, tile
         ordinal, offset in tile) so any distribution of the array holds identical data."""
         self._allocate()
+        dev = self.world.dev
+        if self.memory == "host":  # generate on the device (one RNG implementation), park on the host
+            big = max((self.tile_elems(o) for o in self.tiles), default=0)
+            tmp = dev.alloc(max(big, 1) * 8)
+            for o, buf in self.tiles.items():
+                n = self.tile_elems(o)
+                dev.fill_uniform(tmp, n, seed, o << 32)
+                check(dev.lib.tadev_memcpy_d2h(dev.ctx, buf.ptr, tmp.ptr, n * 8, dev.stream))
+            dev.sync()
+            tmp.free()
+            return self
         for o, buf in self.tiles.items():
-            self.world.dev.fill_uniform(buf, self.tile_elems(o), seed, o << 32)
+            dev.fill_uniform(buf, self.tile_elems(o), seed, o << 32)
         return self
 
     def set(self, ordinal: int, tile: np.ndarray) -> None:
@@ -352,7 +372,10 @@ class DistArray:
         _ta_assert(not self.is_zero(ordinal), "DistArray::set: tile is zero in the shape")
         ext = self.trange.tile_extent(self.trange.tile_index(ordinal))
         _ta_assert(tuple(tile.shape) == tuple(ext), f"DistArray::set: tile extent {tile.shape} != {ext}")
-        self.world.dev.upload_into(self.tiles[ordinal], np.ascontiguousarray(tile, dtype=np.float64))
+        if self.memory == "host":
+            self.tiles[ordinal].numpy(np.float64, ext)[...] = tile
+        else:
+            self.world.dev.upload_into(self.tiles[ordinal], np.ascontiguousarray(tile, dtype=np.float64))
 
     def init_from_numpy(self, full: np.ndarray) -> "DistArray":
         _ta_assert(tuple(full.shape) == self.trange.elements_shape, "init_from_numpy: shape mismatch")
@@ -365,6 +388,8 @@ class DistArray:
         """Local tile as a host array (dist_array.h:717)."""
         _ta_assert(ordinal in self.tiles, "DistArray::find: tile is zero or not local")
         ext = self.trange.tile_extent(self.trange.tile_index(ordinal))
+        if self.memory == "host":
+            return self.tiles[ordinal].numpy(np.float64, ext).copy()
         return self.world.dev.download(self.tiles[ordinal], np.float64, ext)
 
     def to_numpy(self) -> np.ndarray:
@@ -445,6 +470,9 @@ class ContractionStats:
     bcast_bytes: int = 0
     device_ms: float = 0.0
     permute_ms: float = 0.0
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+    row_blocks: int = 1
 
 
 class ContEngine:
@@ -457,6 +485,7 @@ class ContEngine:
     last_stats: Optional[ContractionStats] = None
     depth = 0             # SUMMA pipeline depth in windows (0 = default 2; TA_SUMMA_MAX_DEPTH analogue)
     steps_per_launch = 0  # K steps fused into one grouped-GEMM launch (0 = auto)
+    row_blocks = 0        # result row blocks for host-resident results (0 = auto)
 
     def __init__(self, result: TsrExpr, left: TsrExpr, right: TsrExpr, factor: float):
         self.result, self.left, self.right, self.factor = result, left, right, factor
@@ -508,8 +537,16 @@ class ContEngine:
         A, B, Cres = self.left.array, self.right.array, self.result.array
         A._allocate()
         B._allocate()
+        old_host_arena = None
+        if Cres is not A and Cres is not B:
+            if Cres.memory == "host" and isinstance(Cres._arena, HostBuffer):
+                old_host_arena, Cres._arena = Cres._arena, None  # page-locking is slow: recycle the pinned arena
+            Cres.release()  # hand the old result's memory back to the pool BEFORE allocating the new one
         nc = P.inner_rank
         stats = ContractionStats()
+        _ta_assert(A.memory == "device" or P.perm_left[0] < 0, "host-resident left operand needs an explicit permutation: not supported")
+        _ta_assert(B.memory == "device" or P.perm_right[0] < 0, "host-resident right operand needs an explicit permutation: not supported")
+        _ta_assert(Cres.memory == "device" or P.perm_result[0] < 0, "host-resident result needs a result permutation: not supported")
         with dev.timer() as tperm:
             trA, shA, tilesA, tmpA = self._permuted_operand(A, self._perm(P.perm_left, P.left_rank))
             trB, shB, tilesB, tmpB = self._permuted_operand(B, self._perm(P.perm_right, P.right_rank))
@@ -598,14 +635,27 @@ class ContEngine:
         elems = (m_ext[ci] * n_ext[cj]).astype(np.int64)
         padded = (elems + 1) & ~1
         offs = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
-        arena = dev.alloc(max(int(offs[-1]), 2) * 8)
+        c_on_host = Cres.memory == "host"
+        need_bytes = max(int(offs[-1]), 2) * 8
+        if c_on_host:
+            if old_host_arena is not None and old_host_arena.nbytes >= need_bytes:
+                arena = old_host_arena
+            else:
+                if old_host_arena is not None:
+                    old_host_arena.free()
+                arena = HostBuffer(need_bytes)
+        else:
+            arena = dev.alloc(need_bytes)
         keys = (ci * Nt + cj).astype(np.int64)
         c_tab[keys] = (arena.ptr + offs[:-1] * 8).astype(np.uint64)
         local_c = list(zip(ci.tolist(), cj.tolist()))
         sizes = padded.tolist()
-        gemm_tiles: Dict[int, DeviceBuffer] = {
-            k_: DeviceBuffer(dev, arena.ptr + o_ * 8, e_ * 8, False)
-            for k_, o_, e_ in zip(keys.tolist(), offs[:-1].tolist(), elems.tolist())}
+        if c_on_host:
+            gemm_tiles = {k_: HostBuffer(e_ * 8, arena.ptr + o_ * 8, owned=False)
+                          for k_, o_, e_ in zip(keys.tolist(), offs[:-1].tolist(), elems.tolist())}
+        else:
+            gemm_tiles = {k_: DeviceBuffer(dev, arena.ptr + o_ * 8, e_ * 8, False)
+                          for k_, o_, e_ in zip(keys.tolist(), offs[:-1].tolist(), elems.tolist())}
 
         sp = SummaPlanC()
         sp.Mt, sp.Nt, sp.Kt = Mt, Nt, Kt
@@ -622,10 +672,14 @@ class ContEngine:
         sp.a_tiles, sp.b_tiles, sp.c_tiles = (a_tab.ctypes.data_as(vpp), b_tab.ctypes.data_as(vpp),
                                               c_tab.ctypes.data_as(vpp))
         sp.accumulate, sp.depth, sp.steps_per_launch = 0, ContEngine.depth, ContEngine.steps_per_launch
+        sp.flags = ((_lib.SUMMA_A_ON_HOST if A.memory == "host" else 0) | (_lib.SUMMA_B_ON_HOST if B.memory == "host" else 0) |
+                    (_lib.SUMMA_C_ON_HOST if c_on_host else 0))
+        sp.row_blocks = ContEngine.row_blocks
         st = SummaStatsC()
         check(w.lib.tadev_summa_f64(dev.ctx, C.byref(sp), C.byref(st)))
         stats.nsteps, stats.nsteps_skipped, stats.npairs = st.nsteps, st.nsteps_skipped, st.npairs
         stats.nlaunches, stats.flops, stats.bcast_bytes, stats.device_ms = st.nlaunches, st.flops, st.bcast_bytes, st.device_ms
+        stats.h2d_bytes, stats.d2h_bytes, stats.row_blocks = st.h2d_bytes, st.d2h_bytes, st.row_blocks
         for b in tmpA + tmpB:
             b.free()
 
@@ -682,7 +736,8 @@ class ContEngine:
 
 
 # ---------------------------------------------------------------------------------------------
-def summa_arrays(world: World, trA: TiledRange, trB: TiledRange, shapeA=None, shapeB=None) -> Tuple[DistArray, DistArray]:
+def summa_arrays(world: World, trA: TiledRange, trB: TiledRange, shapeA=None, shapeB=None,
+                 memory: str = "device") -> Tuple[DistArray, DistArray]:
     """Create the operands of ``C[m,n] = A[m,k] * B[k,n]`` (matrices) distributed with the
     process grid's cyclic maps (make_row_phase_pmap / make_col_phase_pmap, proc_grid.h:566-597)
     and with arenas ordered so that SUMMA panels are contiguous."""
@@ -694,4 +749,4 @@ def summa_arrays(world: World, trA: TiledRange, trB: TiledRange, shapeA=None, sh
     ownB = lambda o: ((o // Nt) % Pr) * Pc + (o % Nt) % Pc  # noqa: E731
     orderA = [i * Kt + k for k in range(Kt) for i in range(Mt)]  # column panels contiguous
     orderB = [k * Nt + j for k in range(Kt) for j in range(Nt)]  # row panels contiguous
-    return (DistArray(world, trA, shapeA, ownA, orderA), DistArray(world, trB, shapeB, ownB, orderB))
+    return (DistArray(world, trA, shapeA, ownA, orderA, memory), DistArray(world, trB, shapeB, ownB, orderB, memory))
