@@ -37,7 +37,10 @@
 
 namespace {
 
-constexpr int BM = kGemmBM, BN = kGemmBN, BK = 16, STAGES = 4;
+#ifndef TADEV_WS_STAGES
+#define TADEV_WS_STAGES 4
+#endif
+constexpr int BM = kGemmBM, BN = kGemmBN, BK = 16, STAGES = TADEV_WS_STAGES;
 constexpr int NCONS = 8;  // consumer warps
 // 12 warps = 3 warpgroups: the register file is carved per warpgroup, so the producer group
 // (warp 8 works, 9-11 idle) hands its registers to the two consumer groups via setmaxnreg.
