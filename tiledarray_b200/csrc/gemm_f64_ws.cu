@@ -6,10 +6,10 @@
 // (even leading dimensions — the common case).
 //
 // Structure (one CTA per SM, 288 threads):
-//   warp 8      producer: pulls CTA tiles from a global atomic counter (dynamic scheduling evens
+//   warp 8      producer (warps 9-11 idle, their registers go to the consumers): pulls CTA tiles from a global atomic counter (dynamic scheduling evens
 //               out block-sparse groups of different K), finds the owning group by a
 //               warp-cooperative 32-ary search, and streams operand slabs of 16 k-values into a
-//               4-stage shared-memory ring through the TMA engine, completing on the stage's
+//               3-stage shared-memory ring (2 x 16 k-values per stage) through the TMA engine, completing on the stage's
 //               "full" mbarrier (expect-tx). It runs ahead across tile boundaries, so the next
 //               tile's operands land while the consumers are still in their epilogue.
 //                 * operand stored k-contiguous ([outer][k]: A/N, B/T): ONE tiled-mode TMA
@@ -37,10 +37,13 @@
 
 namespace {
 
-#ifndef TADEV_WS_STAGES
-#define TADEV_WS_STAGES 4
+#ifndef TADEV_WS_SUB
+#define TADEV_WS_SUB 2   // 16-wide k sub-slabs per pipeline stage (one mbarrier round trip per stage)
 #endif
-constexpr int BM = kGemmBM, BN = kGemmBN, BK = 16, STAGES = TADEV_WS_STAGES;
+#ifndef TADEV_WS_STAGES
+#define TADEV_WS_STAGES (TADEV_WS_SUB == 1 ? 4 : 3)
+#endif
+constexpr int BM = kGemmBM, BN = kGemmBN, BK = 16, SUB = TADEV_WS_SUB, STAGES = TADEV_WS_STAGES;
 constexpr int NCONS = 8;  // consumer warps
 // 12 warps = 3 warpgroups: the register file is carved per warpgroup, so the producer group
 // (warp 8 works, 9-11 idle) hands its registers to the two consumer groups via setmaxnreg.
@@ -48,8 +51,9 @@ constexpr int NTHREADS = (NCONS + 4) * 32;
 constexpr int LD_OMAJOR = BM + 4;                // 132 doubles: [k 16][outer 128] padded rows
 constexpr int SLAB_BYTES = 17408;                // >= 16*132*8 (16896) and >= 128*128 (16384); 17 KiB keeps 1 KiB alignment
 constexpr int SLAB_DOUBLES = SLAB_BYTES / 8;
-constexpr int STAGE_DOUBLES = 2 * SLAB_DOUBLES;
-constexpr int SMEM_DATA_BYTES = STAGES * 2 * SLAB_BYTES;  // 139264
+constexpr int SUBSTAGE_DOUBLES = 2 * SLAB_DOUBLES;          // [A slab][B slab] of one 16-wide sub-slab
+constexpr int STAGE_DOUBLES = SUB * SUBSTAGE_DOUBLES;
+constexpr int SMEM_DATA_BYTES = STAGES * SUB * 2 * SLAB_BYTES;  // 3 x 2 x 34816 = 208896
 constexpr int LAST_FLAG = 0x100;
 
 struct WsTask {  // device-side task: public task + tensor maps of its k-contiguous operands
@@ -194,25 +198,41 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
           if (B_KIN) tensormap_acquire(T.mapB);
         }
         __syncwarp();
-        for (int k0 = 0; k0 < K; k0 += BK) {
-          const int kb = min(BK, K - k0);
-          const bool last = (ti == last_task) && (k0 + BK >= K);
+        for (int k0 = 0; k0 < K; k0 += BK * SUB) {
+          const int kb = min(BK * SUB, K - k0);
+          const bool last = (ti == last_task) && (k0 + BK * SUB >= K);
           mbar_wait(&ctrl->empty[stage], phase ^ 1);
-          double* sA = smem + stage * STAGE_DOUBLES;
-          double* sB = sA + SLAB_DOUBLES;
+          double* sStage = smem + stage * STAGE_DOUBLES;
           if (lane == 0) {
             ctrl->kb[stage] = kb | (last ? LAST_FLAG : 0);
-            const uint32_t bytesA = A_KIN ? (uint32_t)(BM * BK * 8) : (uint32_t)(rowsA * kb * 8);
-            const uint32_t bytesB = B_KIN ? (uint32_t)(BN * BK * 8) : (uint32_t)(colsB * kb * 8);
-            mbar_arrive_expect_tx(&ctrl->full[stage], bytesA + bytesB);
-            if (A_KIN) tma_2d_g2s(sA, T.mapA, k0, m0, &ctrl->full[stage]);
-            if (B_KIN) tma_2d_g2s(sB, T.mapB, k0, n0, &ctrl->full[stage]);
+            uint32_t bytes = 0;
+#pragma unroll
+            for (int sub = 0; sub < SUB; ++sub) {
+              const int kbs = min(BK, kb - sub * BK);
+              if (kbs <= 0) break;
+              bytes += A_KIN ? (uint32_t)(BM * BK * 8) : (uint32_t)(rowsA * kbs * 8);
+              bytes += B_KIN ? (uint32_t)(BN * BK * 8) : (uint32_t)(colsB * kbs * 8);
+            }
+            mbar_arrive_expect_tx(&ctrl->full[stage], bytes);
+#pragma unroll
+            for (int sub = 0; sub < SUB; ++sub) {
+              if (kb - sub * BK <= 0) break;
+              double* sA = sStage + sub * SUBSTAGE_DOUBLES;
+              if (A_KIN) tma_2d_g2s(sA, T.mapA, k0 + sub * BK, m0, &ctrl->full[stage]);
+              if (B_KIN) tma_2d_g2s(sA + SLAB_DOUBLES, T.mapB, k0 + sub * BK, n0, &ctrl->full[stage]);
+            }
           }
           __syncwarp();
-          if (!A_KIN && lane < kb)
-            bulk_g2s(sA + lane * LD_OMAJOR, T.A + (size_t)(k0 + lane) * M + m0, rowsA * 8, &ctrl->full[stage]);
-          if (!B_KIN && lane < kb)
-            bulk_g2s(sB + lane * LD_OMAJOR, T.B + (size_t)(k0 + lane) * N + n0, colsB * 8, &ctrl->full[stage]);
+#pragma unroll
+          for (int sub = 0; sub < SUB; ++sub) {
+            const int kbs = min(BK, kb - sub * BK);
+            if (kbs <= 0) break;
+            double* sA = sStage + sub * SUBSTAGE_DOUBLES;
+            double* sB = sA + SLAB_DOUBLES;
+            const int kr = k0 + sub * BK + lane;
+            if (!A_KIN && lane < kbs) bulk_g2s(sA + lane * LD_OMAJOR, T.A + (size_t)kr * M + m0, rowsA * 8, &ctrl->full[stage]);
+            if (!B_KIN && lane < kbs) bulk_g2s(sB + lane * LD_OMAJOR, T.B + (size_t)kr * N + n0, colsB * 8, &ctrl->full[stage]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -244,40 +264,45 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
       for (;;) {
         mbar_wait(&ctrl->full[stage], phase);
         const int flags = ctrl->kb[stage];
-        const int kb = flags & 0xff;
-        const double* sA = smem + stage * STAGE_DOUBLES;
-        const double* sB = sA + SLAB_DOUBLES;
-        // fragment offsets. k-contiguous slab: row R holds 16 doubles; its 16-byte chunk c sits at
-        // chunk (c ^ (R & 7)) (SWIZZLE_128B); rows wm+i*8+g have R & 7 == g.
-        auto kstep = [&](int s, bool masked) {
-          const int kk = kt ^ (2 * s);
-          const int kin_off = ((((kk >> 1) ^ g) << 1) | (kk & 1));
-          const bool valid = !masked || (kk < kb);
-          double a[8], b[4];
+        const int kb_stage = flags & 0xff;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = wm + i * 8 + g;
-            const double v = A_KIN ? sA[row * BK + kin_off] : sA[kk * LD_OMAJOR + row];
-            a[i] = valid ? v : 0.0;
-          }
+        for (int sub = 0; sub < SUB; ++sub) {
+          const int kb = min(BK, kb_stage - sub * BK);  // valid k-values of this sub-slab
+          if (kb <= 0) break;
+          const double* sA = smem + stage * STAGE_DOUBLES + sub * SUBSTAGE_DOUBLES;
+          const double* sB = sA + SLAB_DOUBLES;
+          // fragment offsets. k-contiguous slab: row R holds 16 doubles; its 16-byte chunk c sits at
+          // chunk (c ^ (R & 7)) (SWIZZLE_128B); rows wm+i*8+g have R & 7 == g.
+          auto kstep = [&](int s, bool masked) {
+            const int kk = kt ^ (2 * s);
+            const int kin_off = ((((kk >> 1) ^ g) << 1) | (kk & 1));
+            const bool valid = !masked || (kk < kb);
+            double a[8], b[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = wn + j * 8 + g;
-            const double v = B_KIN ? sB[col * BK + kin_off] : sB[kk * LD_OMAJOR + col];
-            b[j] = valid ? v : 0.0;
-          }
+            for (int i = 0; i < 8; ++i) {
+              const int row = wm + i * 8 + g;
+              const double v = A_KIN ? sA[row * BK + kin_off] : sA[kk * LD_OMAJOR + row];
+              a[i] = valid ? v : 0.0;
+            }
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 4; ++j) {
+              const int col = wn + j * 8 + g;
+              const double v = B_KIN ? sB[col * BK + kin_off] : sB[kk * LD_OMAJOR + col];
+              b[j] = valid ? v : 0.0;
+            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        };
-        if (kb == BK) {
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int s = 0; s < 4; ++s) kstep(s, false);
-        } else if (kb > 0) {
-          // K tail: stale rows of an outer-contiguous slab are masked to zero on both operands
+              for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          };
+          if (kb == BK) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) kstep(s, false);
+          } else {
+            // K tail: stale rows of an outer-contiguous slab are masked to zero on both operands
 #pragma unroll 1
-          for (int s = 0; s < 4; ++s) kstep(s, true);
+            for (int s = 0; s < 4; ++s) kstep(s, true);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctrl->empty[stage]);
