@@ -48,16 +48,19 @@ extern "C" int tadev_comm_init(tadev_ctx* ctx, const void* unique_id128, int ran
   TADEV_CHECK_CUDA(cudaSetDevice(ctx->device));
   ncclUniqueId id;
   memcpy(&id, unique_id128, sizeof(id));
-  TADEV_CHECK_NCCL(ncclCommInitRank(&ctx->world, nranks, id, rank));
-  ctx->rank = rank; ctx->nranks = nranks; ctx->Pr = Pr; ctx->Pc = Pc;
-  // leave a few SMs to NCCL's broadcast CTAs so panel traffic overlaps the persistent GEMM
+  // The persistent GEMM leaves `gemm_sm_reserve` SMs free and NCCL is capped to as many CTAs, so the
+  // panel broadcasts of window w+1 are always resident next to the GEMM of window w.
   ctx->gemm_sm_reserve = (Pr * Pc > 1) ? 4 : 0;
   if (const char* e = getenv("TADEV_SM_RESERVE")) ctx->gemm_sm_reserve = atoi(e);
+  ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+  if (ctx->gemm_sm_reserve > 0) { cfg.minCTAs = 1; cfg.maxCTAs = ctx->gemm_sm_reserve; }
+  TADEV_CHECK_NCCL(ncclCommInitRankConfig(&ctx->world, nranks, id, rank, &cfg));
+  ctx->rank = rank; ctx->nranks = nranks; ctx->Pr = Pr; ctx->Pc = Pc;
   const bool in_grid = rank < Pr * Pc;
   ctx->my_r = in_grid ? rank / Pc : -1;  // proc_grid.h: rank_row = rank / proc_cols
   ctx->my_c = in_grid ? rank % Pc : -1;
-  TADEV_CHECK_NCCL(ncclCommSplit(ctx->world, in_grid ? ctx->my_r : NCCL_SPLIT_NOCOLOR, ctx->my_c, &ctx->row_comm, nullptr));
-  TADEV_CHECK_NCCL(ncclCommSplit(ctx->world, in_grid ? ctx->my_c : NCCL_SPLIT_NOCOLOR, ctx->my_r, &ctx->col_comm, nullptr));
+  TADEV_CHECK_NCCL(ncclCommSplit(ctx->world, in_grid ? ctx->my_r : NCCL_SPLIT_NOCOLOR, ctx->my_c, &ctx->row_comm, &cfg));
+  TADEV_CHECK_NCCL(ncclCommSplit(ctx->world, in_grid ? ctx->my_c : NCCL_SPLIT_NOCOLOR, ctx->my_r, &ctx->col_comm, &cfg));
   return TADEV_OK;
 }
 
