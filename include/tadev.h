@@ -93,7 +93,11 @@ typedef struct {
   int32_t task_begin; /* first task of this group */
   int32_t task_end;   /* one past the last task */
   int32_t accumulate; /* 0: C = alpha*sum ; 1: C += alpha*sum */
-  int32_t reserved;
+  /* optional L2 rasterisation hint: 0 = none, else ((row0+1) << 16) | (col0+1) where (row0, col0)
+   * is the origin of this result tile in a global grid of 128x128 blocks of the whole result
+   * matrix. When every group of a launch carries a hint, CTAs walk the result in square
+   * super-blocks so that operand panels are shared through L2 (see gemm_f64_ws.cu). */
+  int32_t raster;
 } tadev_gemm_group;
 
 /* h_groups/h_tasks are HOST arrays; the call copies them to the device on `s` (staging is
@@ -194,6 +198,11 @@ typedef struct {
 } tadev_contraction_plan;
 int tadev_plan_contraction(const char* target, const char* left, const char* right,
                            tadev_contraction_plan* out);
+/* Same, but also plans the operand-exchanged product (C^T = B^T A^T) and returns it with
+ * *swapped = 1 when it needs fewer explicit tile permutations; the caller then passes the arrays
+ * in exchanged order. The reference has no such step (it permutes result tiles instead). */
+int tadev_plan_contraction_opt(const char* target, const char* left, const char* right,
+                               tadev_contraction_plan* out, int32_t* swapped);
 
 /* ---- multi-GPU: communicators + SUMMA driver ------------------------------------------------
  * replaces detail::Summa (dist_eval/contraction_eval.h:55-2027) and its world.gop.bcast
@@ -275,6 +284,9 @@ int tadev_summa_steps(int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt, cons
 int tadev_probe_fp64_peak(tadev_ctx* ctx, int kind /*0 dmma, 1 dfma, 2 both*/, int iters,
                           double* tflops, float* ms);
 int tadev_probe_copy_gbs(tadev_ctx* ctx, size_t bytes, int iters, double* gbs);
+/* pinned-host <-> device copy rates (GB/s): each direction alone and both at once */
+int tadev_probe_pcie_gbs(tadev_ctx* ctx, size_t bytes, double* h2d, double* d2h, double* h2d_bidir,
+                         double* d2h_bidir);
 /* number of kernels this library launched since init (bench.py's gpu_launches) */
 int tadev_launch_count(tadev_ctx* ctx, int64_t* n);
 

@@ -28,7 +28,7 @@ class GemmTask(C.Structure):
 
 class GemmGroup(C.Structure):
     _fields_ = [("C", C.c_void_p), ("m", C.c_int32), ("n", C.c_int32), ("task_begin", C.c_int32),
-                ("task_end", C.c_int32), ("accumulate", C.c_int32), ("reserved", C.c_int32)]
+                ("task_end", C.c_int32), ("accumulate", C.c_int32), ("raster", C.c_int32)]
 
 
 class ProcGridC(C.Structure):
@@ -105,6 +105,7 @@ PROTOTYPES = {
     "tadev_proc_grid_make": (_i, [_i, _i, _i64, _i64, _i64, _i64, _P(ProcGridC)]),
     "tadev_cyclic_owner": (_i, [_i64, _i64, _i, _i, _P(_i)]),
     "tadev_plan_contraction": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, _P(ContractionPlanC)]),
+    "tadev_plan_contraction_opt": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, _P(ContractionPlanC), _P(C.c_int32)]),
     "tadev_comm_unique_id": (_i, [_vp]),
     "tadev_comm_init": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "tadev_comm_destroy": (_i, [_vp]),
@@ -116,6 +117,7 @@ PROTOTYPES = {
                                _P(C.c_int32)]),
     "tadev_probe_fp64_peak": (_i, [_vp, _i, _i, _P(_d), _P(_f)]),
     "tadev_probe_copy_gbs": (_i, [_vp, _sz, _i, _P(_d)]),
+    "tadev_probe_pcie_gbs": (_i, [_vp, _sz, _P(_d), _P(_d), _P(_d), _P(_d)]),
     "tadev_launch_count": (_i, [_vp, _P(_i64)]),
 }
 

@@ -75,7 +75,7 @@ int launch_gemm_grouped_f64(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, do
 // fast path (host descriptors; stages them, resolves tensor maps, launches the persistent kernel)
 int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, double alpha,
                                const tadev_gemm_group* h_groups, int ngroups, const tadev_gemm_task* h_tasks,
-                               int ntasks, const int32_t* h_prefix, int total_cta_tiles);
+                               int ntasks, int total_cta_tiles);
 void tadev_tmap_cache_destroy(tadev_ctx* ctx);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

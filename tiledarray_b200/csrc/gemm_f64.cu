@@ -314,8 +314,7 @@ extern "C" int tadev_gemm_grouped_f64(tadev_ctx* ctx, tadev_stream s_, int opA, 
   if (total == 0) return TADEV_OK;
   const bool al = batch_aligned16(opA, opB, h_groups, ngroups, h_tasks);
   if (al && !ctx->force_generic_gemm)  // fast path: persistent warp-specialised TMA kernel
-    return launch_gemm_grouped_f64_ws(ctx, s, opA, opB, alpha, h_groups, ngroups, h_tasks, ntasks, prefix.data(),
-                                      (int)total);
+    return launch_gemm_grouped_f64_ws(ctx, s, opA, opB, alpha, h_groups, ngroups, h_tasks, ntasks, (int)total);
   const size_t gb = sizeof(tadev_gemm_group) * (size_t)ngroups;
   const size_t tb = sizeof(tadev_gemm_task) * (size_t)ntasks;
   const size_t pb = sizeof(int32_t) * (size_t)(ngroups + 1);

@@ -31,6 +31,7 @@
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <unordered_map>
 
 #include "common.h"
@@ -123,8 +124,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <int OPA, int OPB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngroups,
-                           const WsTask* __restrict__ tasks, const int32_t* __restrict__ tile_prefix,
-                           int total_tiles, int* __restrict__ tile_counter, double alpha) {
+                           const WsTask* __restrict__ tasks, const int2* __restrict__ items,
+                           int total_tiles, int* __restrict__ tile_counter, double alpha, int static_sched) {
   constexpr bool A_KIN = (OPA == TADEV_OP_N);  // A stored [m][k]
   constexpr bool B_KIN = (OPB == TADEV_OP_T);  // B stored [n][k]
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -148,31 +149,20 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
     for (int it = 0;; ++it) {
       const int slot = it & 1;
       mbar_wait(&ctrl->sched_empty[slot], ((it >> 1) & 1) ^ 1);
-      int w = 0;
-      if (lane == 0) w = atomicAdd(tile_counter, 1);
-      w = __shfl_sync(0xffffffffu, w, 0);
+      int w = it * (int)gridDim.x + (int)blockIdx.x;
+      if (!static_sched) {
+        if (lane == 0) w = atomicAdd(tile_counter, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+      }
       if (w >= total_tiles) {
         if (lane == 0) { ctrl->sched_group[slot] = -1; mbar_arrive(&ctrl->sched_full[slot]); }
         break;
       }
-      // warp-cooperative 32-ary search: the g with tile_prefix[g] <= w < tile_prefix[g+1]
-      int lo = 0, hi = ngroups;
-      while (hi - lo > 1) {
-        const int step = (hi - lo + 31) / 32;
-        const int probe = lo + lane * step;
-        const bool le = (probe < hi) && (__ldg(tile_prefix + probe) <= w);
-        const unsigned m = __ballot_sync(0xffffffffu, le);
-        const int last = 31 - __clz(m);  // lane 0 always qualifies
-        const int nlo = lo + last * step;
-        int nhi = nlo + step;
-        if (nhi > hi) nhi = hi;
-        lo = nlo; hi = nhi;
-      }
-      const int gi = lo;
+      // work item w of the rasterised order (host-built, see raster_items): group + 128x128 block
+      const int2 item = __ldg(items + w);
+      const int gi = item.x;
       const tadev_gemm_group grp = groups[gi];
-      const int local = w - __ldg(tile_prefix + gi);
-      const int tiles_n = (grp.n + BN - 1) / BN;
-      const int m0 = (local / tiles_n) * BM, n0 = (local % tiles_n) * BN;
+      const int m0 = (int)((unsigned)item.y >> 16) * BM, n0 = (item.y & 0xffff) * BN;
       if (lane == 0) {
         ctrl->sched_group[slot] = gi; ctrl->sched_m0[slot] = m0; ctrl->sched_n0[slot] = n0;
         mbar_arrive(&ctrl->sched_full[slot]);
@@ -412,6 +402,10 @@ int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* group
   std::lock_guard<std::mutex> lk(c->mu);
   struct Pending { CUtensorMap* dst; int stage_idx; };
   std::vector<Pending> pending;
+  static const int promo_env = getenv("TADEV_TMAP_L2PROMO") ? atoi(getenv("TADEV_TMAP_L2PROMO")) : 3;
+  const CUtensorMapL2promotion l2promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   auto lookup = [&](const double* ptr, int outer, int k, const CUtensorMap** res) -> int {
     TmapKey key{ptr, outer, k};
     auto itf = c->index.find(key);
@@ -436,7 +430,7 @@ int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* group
     const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = c->encode(hm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2promo,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
       tadev_set_error("cuTensorMapEncodeTiled failed (%d) for tile %p [%d x %d]", (int)cr, (const void*)ptr, outer, k);
@@ -475,14 +469,14 @@ int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* group
 
 template <int OPA, int OPB>
 int launch_ws_variant(cudaStream_t s, int grid, const tadev_gemm_group* d_groups, int ngroups, const WsTask* d_tasks,
-                      const int32_t* d_tile_prefix, int total_tiles, int* d_counter, double alpha) {
+                      const int2* d_items, int total_tiles, int* d_counter, double alpha, int static_sched) {
   auto kern = gemm_grouped_f64_ws_kernel<OPA, OPB>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
     TADEV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, NTHREADS, SMEM_BYTES, s>>>(d_groups, ngroups, d_tasks, d_tile_prefix, total_tiles, d_counter, alpha);
+  kern<<<grid, NTHREADS, SMEM_BYTES, s>>>(d_groups, ngroups, d_tasks, d_items, total_tiles, d_counter, alpha, static_sched);
   TADEV_CHECK_CUDA(cudaGetLastError());
   return TADEV_OK;
 }
@@ -499,14 +493,86 @@ void tadev_tmap_cache_destroy(tadev_ctx* ctx) {
   ctx->tmap_cache = nullptr;
 }
 
+namespace {
+
+// Work-item order of the persistent kernel. Item = (group, 128x128 block of its result tile); the
+// CTAs pull items in this order from an atomic counter, so the ~num_SMs items in flight at any time
+// are `grid` consecutive entries. Groups that carry a raster hint (tadev_gemm_group::raster: origin
+// of the result tile in a global grid of 128x128 blocks) are ordered in bands of S = floor(sqrt(grid))
+// block rows, column-major inside a band: a wave then covers ~S x S blocks, i.e. S block-rows of A
+// and S block-columns of B are shared through L2 instead of 8 x 8 per result tile (DRAM traffic of
+// the N=32768 launch: 1.19 TB group-major). Without hints the order is group-major.
+void raster_items(const tadev_gemm_group* groups, int ngroups, int grid, int2* items, int total) {
+  bool hinted = ngroups > 1 && !(getenv("TADEV_RASTER_S") && atoi(getenv("TADEV_RASTER_S")) == 0);
+  for (int gi = 0; gi < ngroups && hinted; ++gi) hinted = groups[gi].raster != 0 || groups[gi].m == 0 || groups[gi].n == 0;
+  int w = 0;
+  if (!hinted) {
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const int tm = (int)ceil_div64(groups[gi].m, BM), tn = (int)ceil_div64(groups[gi].n, BN);
+      for (int a = 0; a < tm; ++a)
+        for (int b = 0; b < tn; ++b) items[w++] = make_int2(gi, (a << 16) | b);
+    }
+    return;
+  }
+  int S = 1;
+  while ((S + 1) * (S + 1) <= grid) ++S;
+  static const int env_S = getenv("TADEV_RASTER_S") ? atoi(getenv("TADEV_RASTER_S")) : -1;
+  static const bool row_major = getenv("TADEV_RASTER_ROWMAJOR") && atoi(getenv("TADEV_RASTER_ROWMAJOR"));
+  if (env_S > 0) S = env_S;
+  int rows = 0, cols = 0;
+  for (int gi = 0; gi < ngroups; ++gi) {
+    if (!groups[gi].raster) continue;
+    const int r0 = (int)((uint32_t)groups[gi].raster >> 16) - 1, c0 = (groups[gi].raster & 0xffff) - 1;
+    rows = std::max(rows, r0 + (int)ceil_div64(groups[gi].m, BM));
+    cols = std::max(cols, c0 + (int)ceil_div64(groups[gi].n, BN));
+  }
+  // key = (band, global block column, row inside the band): dense integers -> counting sort
+  const int64_t nkeys = row_major ? (int64_t)ceil_div64(cols, S) * rows * S : (int64_t)ceil_div64(rows, S) * cols * S;
+  auto key_of = [&](int gr, int gc) {
+    return row_major ? ((int64_t)(gc / S) * rows + gr) * S + gc % S : ((int64_t)(gr / S) * cols + gc) * S + gr % S;
+  };
+  if (nkeys <= 16 * (int64_t)total + 4096) {
+    std::vector<int32_t> start((size_t)nkeys + 1, 0);
+    for (int gi = 0; gi < ngroups; ++gi) {
+      if (!groups[gi].raster) continue;
+      const int r0 = (int)((uint32_t)groups[gi].raster >> 16) - 1, c0 = (groups[gi].raster & 0xffff) - 1;
+      const int tm = (int)ceil_div64(groups[gi].m, BM), tn = (int)ceil_div64(groups[gi].n, BN);
+      for (int a = 0; a < tm; ++a)
+        for (int b = 0; b < tn; ++b) ++start[(size_t)key_of(r0 + a, c0 + b) + 1];
+    }
+    for (int64_t k = 0; k < nkeys; ++k) start[k + 1] += start[k];
+    for (int gi = 0; gi < ngroups; ++gi) {
+      if (!groups[gi].raster) continue;
+      const int r0 = (int)((uint32_t)groups[gi].raster >> 16) - 1, c0 = (groups[gi].raster & 0xffff) - 1;
+      const int tm = (int)ceil_div64(groups[gi].m, BM), tn = (int)ceil_div64(groups[gi].n, BN);
+      for (int a = 0; a < tm; ++a)
+        for (int b = 0; b < tn; ++b) items[start[key_of(r0 + a, c0 + b)]++] = make_int2(gi, (a << 16) | b);
+    }
+    return;
+  }
+  std::vector<std::pair<int64_t, int2>> keyed;
+  keyed.reserve(total);
+  for (int gi = 0; gi < ngroups; ++gi) {
+    if (!groups[gi].raster) continue;
+    const int r0 = (int)((uint32_t)groups[gi].raster >> 16) - 1, c0 = (groups[gi].raster & 0xffff) - 1;
+    const int tm = (int)ceil_div64(groups[gi].m, BM), tn = (int)ceil_div64(groups[gi].n, BN);
+    for (int a = 0; a < tm; ++a)
+      for (int b = 0; b < tn; ++b) keyed.push_back({key_of(r0 + a, c0 + b), make_int2(gi, (a << 16) | b)});
+  }
+  std::stable_sort(keyed.begin(), keyed.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+  for (auto& kv : keyed) items[w++] = kv.second;
+}
+
+}  // namespace
+
 // Host-descriptor entry of the fast path: builds device descriptors (+ tensor maps) and launches.
 int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, double alpha,
                                const tadev_gemm_group* h_groups, int ngroups, const tadev_gemm_task* h_tasks,
-                               int ntasks, const int32_t* h_prefix, int total_cta_tiles) {
+                               int ntasks, int total_cta_tiles) {
   if (ngroups == 0 || total_cta_tiles == 0) return TADEV_OK;
   const size_t gb = sizeof(tadev_gemm_group) * (size_t)ngroups;
   const size_t tb = sizeof(WsTask) * (size_t)ntasks;
-  const size_t pb = sizeof(int32_t) * (size_t)(ngroups + 1);
+  const size_t pb = sizeof(int2) * (size_t)total_cta_tiles;
   const size_t off_t = (gb + 15) & ~size_t(15);
   const size_t off_p = (off_t + tb + 15) & ~size_t(15);
   const size_t off_c = (off_p + pb + 15) & ~size_t(15);
@@ -517,22 +583,23 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
   memcpy(h, h_groups, gb);
   rc = resolve_maps(ctx, opA, opB, h_groups, ngroups, h_tasks, (WsTask*)((char*)h + off_t));
   if (rc) return rc;
-  memcpy((char*)h + off_p, h_prefix, pb);
-  memset((char*)h + off_c, 0, 16);
-  TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, off_c + 16, cudaMemcpyHostToDevice, s));
-  ctx->launches++;
   int grid = ctx->num_sms - ctx->gemm_sm_reserve;
   if (grid < 1) grid = 1;
   if (grid > total_cta_tiles) grid = total_cta_tiles;
+  raster_items(h_groups, ngroups, grid, (int2*)((char*)h + off_p), total_cta_tiles);
+  static const int static_sched = getenv("TADEV_SCHED_STATIC") ? atoi(getenv("TADEV_SCHED_STATIC")) : 0;
+  memset((char*)h + off_c, 0, 16);
+  TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, off_c + 16, cudaMemcpyHostToDevice, s));
+  ctx->launches++;
   const tadev_gemm_group* dg = (const tadev_gemm_group*)d;
   const WsTask* dt = (const WsTask*)((char*)d + off_t);
-  const int32_t* dp = (const int32_t*)((char*)d + off_p);
+  const int2* dp = (const int2*)((char*)d + off_p);
   int* dc = (int*)((char*)d + off_c);
   switch ((opA << 1) | opB) {
-    case 0: rc = launch_ws_variant<0, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha); break;
-    case 1: rc = launch_ws_variant<0, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha); break;
-    case 2: rc = launch_ws_variant<1, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha); break;
-    case 3: rc = launch_ws_variant<1, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha); break;
+    case 0: rc = launch_ws_variant<0, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched); break;
+    case 1: rc = launch_ws_variant<0, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched); break;
+    case 2: rc = launch_ws_variant<1, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched); break;
+    case 3: rc = launch_ws_variant<1, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched); break;
     default: tadev_set_error("launch_gemm_grouped_f64_ws: bad op flags %d %d", opA, opB); rc = TADEV_EINVAL;
   }
   TADEV_CHECK_CUDA(cudaEventRecord(done, s));

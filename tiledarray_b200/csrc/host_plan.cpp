@@ -198,6 +198,29 @@ extern "C" int tadev_plan_contraction(const char* target, const char* left, cons
   return TADEV_OK;
 }
 
+// The reference always produces the result in (left outer, right outer) order and permutes every
+// result tile when the target order differs (contract_reduce.h:370-378). C = A*B and C^T = B^T*A^T
+// are the same set of products summed in the same k order, so the engine may exchange the
+// operands when that removes explicit tile permutations (BASELINE config 4:
+// R("a,b,i,j") = T("c,d,i,j") * V("a,b,c,d") is a plain NN product V*T with no permutation at all,
+// but two transposed operands plus a result permutation as written).
+extern "C" int tadev_plan_contraction_opt(const char* target, const char* left, const char* right,
+                                          tadev_contraction_plan* out, int32_t* swapped) {
+  TADEV_REQUIRE(out && swapped, "tadev_plan_contraction_opt: null");
+  tadev_contraction_plan a, b;
+  int rc = tadev_plan_contraction(target, left, right, &a);
+  if (rc) return rc;
+  *out = a;
+  *swapped = 0;
+  auto cost = [](const tadev_contraction_plan& p) {
+    return (p.perm_left[0] >= 0) + (p.perm_right[0] >= 0) + (p.perm_result[0] >= 0);
+  };
+  if (cost(a) == 0 || a.inner_rank == 0) return TADEV_OK;
+  if (tadev_plan_contraction(target, right, left, &b) != TADEV_OK) return TADEV_OK;
+  if (cost(b) < cost(a)) { *out = b; *swapped = 1; }
+  return TADEV_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // SUMMA schedule
 SummaSchedule make_summa_schedule(int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt, const float* a,

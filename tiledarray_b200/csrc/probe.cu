@@ -112,3 +112,41 @@ extern "C" int tadev_probe_copy_gbs(tadev_ctx* ctx, size_t bytes, int iters, dou
   cudaFree(b);
   return TADEV_OK;
 }
+
+// Pinned-host <-> device copy rates: h2d alone, d2h alone, and both directions at once (the e2e
+// leg of bench.py streams operands in while result blocks stream out).
+extern "C" int tadev_probe_pcie_gbs(tadev_ctx* ctx, size_t bytes, double* h2d, double* d2h, double* h2d_bidir,
+                                    double* d2h_bidir) {
+  TADEV_REQUIRE(ctx && bytes >= 4096, "tadev_probe_pcie_gbs: bad args");
+  cudaStream_t s0 = ctx->comm_stream[1], s1 = ctx->streams[ctx->streams.size() > 1 ? 1 : 0];
+  void *h0 = nullptr, *h1 = nullptr, *d0 = nullptr, *d1 = nullptr;
+  TADEV_CHECK_CUDA(cudaMallocHost(&h0, bytes));
+  TADEV_CHECK_CUDA(cudaMallocHost(&h1, bytes));
+  TADEV_CHECK_CUDA(cudaMalloc(&d0, bytes));
+  TADEV_CHECK_CUDA(cudaMalloc(&d1, bytes));
+  memset(h0, 1, bytes);
+  memset(h1, 2, bytes);
+  cudaEvent_t e[4];
+  for (auto& x : e) TADEV_CHECK_CUDA(cudaEventCreate(&x));
+  auto timed = [&](bool up, bool down, float* t_up, float* t_down) -> int {
+    TADEV_CHECK_CUDA(cudaDeviceSynchronize());
+    if (up) { TADEV_CHECK_CUDA(cudaEventRecord(e[0], s0)); TADEV_CHECK_CUDA(cudaMemcpyAsync(d0, h0, bytes, cudaMemcpyHostToDevice, s0)); TADEV_CHECK_CUDA(cudaEventRecord(e[1], s0)); }
+    if (down) { TADEV_CHECK_CUDA(cudaEventRecord(e[2], s1)); TADEV_CHECK_CUDA(cudaMemcpyAsync(h1, d1, bytes, cudaMemcpyDeviceToHost, s1)); TADEV_CHECK_CUDA(cudaEventRecord(e[3], s1)); }
+    TADEV_CHECK_CUDA(cudaDeviceSynchronize());
+    if (up) TADEV_CHECK_CUDA(cudaEventElapsedTime(t_up, e[0], e[1]));
+    if (down) TADEV_CHECK_CUDA(cudaEventElapsedTime(t_down, e[2], e[3]));
+    return TADEV_OK;
+  };
+  float tu = 0, td = 0;
+  int rc = timed(true, true, &tu, &td);  // warm-up
+  if (!rc) rc = timed(true, false, &tu, &td);
+  if (!rc && h2d) *h2d = bytes / (tu * 1e-3) / 1e9;
+  if (!rc) rc = timed(false, true, &tu, &td);
+  if (!rc && d2h) *d2h = bytes / (td * 1e-3) / 1e9;
+  if (!rc) rc = timed(true, true, &tu, &td);
+  if (!rc && h2d_bidir) *h2d_bidir = bytes / (tu * 1e-3) / 1e9;
+  if (!rc && d2h_bidir) *d2h_bidir = bytes / (td * 1e-3) / 1e9;
+  for (auto& x : e) cudaEventDestroy(x);
+  cudaFreeHost(h0); cudaFreeHost(h1); cudaFree(d0); cudaFree(d1);
+  return rc;
+}

@@ -292,6 +292,27 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   TADEV_CHECK_CUDA(cudaStreamWaitEvent(sh, ev_start, 0));
   TADEV_CHECK_CUDA(cudaStreamWaitEvent(sd, ev_start, 0));
 
+  // origin of every local result tile in this rank's grid of 128x128 blocks (L2 rasterisation hint)
+  std::vector<int32_t> blk_row0(Mt, 0), blk_col0(Nt, 0);
+  {
+    int64_t o = 0;
+    for (int i = r; i < Mt; i += Pr) { blk_row0[i] = (int32_t)o; o += ceil_div64(P.m_ext[i], kGemmBM); }
+    bool ok = o < 65535;
+    o = 0;
+    for (int j = c; j < Nt; j += Pc) { blk_col0[j] = (int32_t)o; o += ceil_div64(P.n_ext[j], kGemmBN); }
+    if (!ok || o >= 65535) { blk_row0.clear(); blk_col0.clear(); }  // too large to encode: no hints
+  }
+  // TADEV_SUMMA_TRACE=1: per-window timeline (ms since the start) of staging, GEMM and download
+  static const bool trace = getenv("TADEV_SUMMA_TRACE") && atoi(getenv("TADEV_SUMMA_TRACE"));
+  struct Mark { const char* what; int block, window; cudaEvent_t ev; };
+  std::vector<Mark> marks;
+  auto mark = [&](const char* what, int blk, int win, cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    marks.push_back({what, blk, win, e});
+  };
   std::vector<char> touched((size_t)Mt * Nt, 0);
   int64_t npairs = 0, nlaunches = 0, bcast_bytes = 0, h2d_bytes = 0, d2h_bytes = 0;
   double flops = 0.0;
@@ -444,6 +465,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
       }
       // ---- ordering: H2D (sh) -> broadcasts (sc) -> GEMM (s0)
       if (any_h2d) {
+        mark("h2d_done", b, wi, sh);
         TADEV_CHECK_CUDA(cudaEventRecord(h2d_done[d], sh));
         TADEV_CHECK_CUDA(cudaStreamWaitEvent(any_bcast ? sc : s0, h2d_done[d], 0));
       }
@@ -492,7 +514,8 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
             TADEV_REQUIRE(ct, "tadev_summa_f64: result tile (%d,%d) is non-zero and local but has no storage", i, j);
             if (!groups.empty()) groups.back().task_end = (int32_t)tasks.size();
             tadev_gemm_group G{ct, (int32_t)P.m_ext[i], (int32_t)P.n_ext[j], (int32_t)tasks.size(), 0,
-                               (P.accumulate || touched[contrib[n].key]) ? 1 : 0, 0};
+                               (P.accumulate || touched[contrib[n].key]) ? 1 : 0,
+                               blk_row0.empty() ? 0 : (int32_t)((uint32_t)(blk_row0[i] + 1) << 16 | (uint32_t)(blk_col0[j] + 1))};
             touched[contrib[n].key] = 1;
             groups.push_back(G);
           }
@@ -503,6 +526,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
                                         (int)tasks.size());
         if (rc) return rc;
         ++nlaunches;
+        mark("gemm_done", b, wi, s0);
       }
       if (need_ring && win.bytes > 0) {
         TADEV_CHECK_CUDA(cudaEventRecord(buf_free[d], s0));
@@ -528,6 +552,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
           TADEV_CHECK_CUDA(cudaMemcpyAsync(P.c_tiles[key], c_dev[key], e * 8, cudaMemcpyDeviceToHost, sd));
           d2h_bytes += (int64_t)e * 8;
         }
+      mark("d2h_done", b, -1, sd);
       TADEV_CHECK_CUDA(cudaEventRecord(d2h_done[cslot], sd));
       c_used[cslot] = true;
     }
@@ -550,6 +575,13 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   TADEV_CHECK_CUDA(cudaGetLastError());
   float ms = 0;
   TADEV_CHECK_CUDA(cudaEventElapsedTime(&ms, ev_start, ev_end));
+  for (auto& mk : marks) {
+    float t = 0;
+    cudaEventSynchronize(mk.ev);
+    cudaEventElapsedTime(&t, ev_start, mk.ev);
+    fprintf(stderr, "[tadev summa rank %d] %-9s block %d window %2d  t=%9.3f ms\n", ctx->rank, mk.what, mk.block, mk.window, t);
+    cudaEventDestroy(mk.ev);
+  }
   if (stats) {
     stats->nsteps = (int64_t)S.steps.size();
     stats->nsteps_skipped = S.nskipped;

@@ -275,6 +275,11 @@ class Device:
         check(self.lib.tadev_probe_copy_gbs(self.ctx, nbytes, iters, C.byref(g)))
         return g.value
 
+    def probe_pcie_gbs(self, nbytes: int = 1 << 30) -> dict:
+        v = [C.c_double() for _ in range(4)]
+        check(self.lib.tadev_probe_pcie_gbs(self.ctx, nbytes, *[C.byref(x) for x in v]))
+        return dict(zip(("h2d", "d2h", "h2d_bidir", "d2h_bidir"), (x.value for x in v)))
+
     def launch_count(self) -> int:
         n = C.c_int64()
         check(self.lib.tadev_launch_count(self.ctx, C.byref(n)))

@@ -486,14 +486,21 @@ class ContEngine:
     depth = 0             # SUMMA pipeline depth in windows (0 = default 2; TA_SUMMA_MAX_DEPTH analogue)
     steps_per_launch = 0  # K steps fused into one grouped-GEMM launch (0 = auto)
     row_blocks = 0        # result row blocks for host-resident results (0 = auto)
+    exchange_operands = True  # evaluate C^T = B^T A^T when that needs fewer explicit tile permutations
 
     def __init__(self, result: TsrExpr, left: TsrExpr, right: TsrExpr, factor: float):
         self.result, self.left, self.right, self.factor = result, left, right, factor
         self.world = left.array.world
         self.dev = self.world.dev
         plan = ContractionPlanC()
-        check(self.world.lib.tadev_plan_contraction(",".join(result.indices).encode(), ",".join(left.indices).encode(),
-                                                    ",".join(right.indices).encode(), C.byref(plan)))
+        tgt, li, ri = (",".join(x.indices).encode() for x in (result, left, right))
+        if ContEngine.exchange_operands:
+            swapped = C.c_int32(0)
+            check(self.world.lib.tadev_plan_contraction_opt(tgt, li, ri, C.byref(plan), C.byref(swapped)))
+            if swapped.value:
+                self.left, self.right = right, left
+        else:
+            check(self.world.lib.tadev_plan_contraction(tgt, li, ri, C.byref(plan)))
         self.plan = plan
 
     @staticmethod
