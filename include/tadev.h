@@ -214,6 +214,15 @@ int tadev_comm_destroy(tadev_ctx* ctx);
 /* which=0: row communicator (A panels), which=1: column communicator (B panels). */
 int tadev_bcast_panel(tadev_ctx* ctx, tadev_stream s, int which, int root, void* d_buf, size_t bytes);
 
+/* Lazy operands (the analogue of TiledArray's lazy tiles: dist_eval/array_eval.h:42 LazyArrayTile,
+ * evaluated when the contraction asks for them): the tile table of a lazy operand holds opaque
+ * non-zero TOKENS instead of pointers, and the driver asks the provider to materialise the `ntiles`
+ * tiles tokens[0..ntiles) at d_dst[0..ntiles) (elems[n] doubles each, row-major in the operand's GEMM
+ * layout) by enqueueing work on stream s. Used for argument permutations performed just in time per
+ * SUMMA window (no permuted copy of the operand) and for tensors generated on the fly. */
+typedef int (*tadev_tile_provider)(void* user, tadev_stream s, int ntiles, const uint64_t* tokens,
+                                   double* const* d_dst, const size_t* elems);
+
 typedef struct {
   int32_t Mt, Nt, Kt;       /* fused tile-grid extents of C (Mt x Nt) and the contraction (Kt) */
   const int64_t* m_ext;     /* [Mt] fused element extent of each tile row      (host) */
@@ -241,12 +250,36 @@ typedef struct {
    * copy stream, overlapped with the GEMM of the previous window; a host result is produced in
    * row blocks, each copied back while the next block computes. Also the out-of-core path. */
   int32_t flags;
-  int32_t row_blocks;       /* result row blocks when the result is on the host (0 = auto) */
+  int32_t row_blocks;       /* result row blocks (0 = auto: 1 for device-resident operands) */
   int32_t reserved;
+  /* TADEV_SUMMA_*_LAZY: tile providers of lazy operands (see tadev_tile_provider) */
+  tadev_tile_provider a_provider;
+  void* a_user;
+  tadev_tile_provider b_provider;
+  void* b_user;
 } tadev_summa_plan;
 #define TADEV_SUMMA_A_ON_HOST 1
 #define TADEV_SUMMA_B_ON_HOST 2
 #define TADEV_SUMMA_C_ON_HOST 4
+#define TADEV_SUMMA_A_LAZY 8
+#define TADEV_SUMMA_B_LAZY 16
+
+/* built-in providers. token = index + 1 into the source's tables. */
+typedef struct {
+  tadev_ctx* ctx;
+  uint64_t seed;            /* tile `index` is filled by tadev_fill_uniform_f64(seed, offset = index << 32) */
+} tadev_uniform_source;
+int tadev_provider_uniform(void* uniform_source, tadev_stream s, int ntiles, const uint64_t* tokens,
+                           double* const* d_dst, const size_t* elems);
+typedef struct {
+  tadev_ctx* ctx;
+  int32_t rank;
+  int32_t perm[16];         /* image form, as tadev_permute */
+  const int64_t* extents;   /* [ntable][rank] extents of each source tile (host) */
+  const void* const* src;   /* [ntable] device pointers of the source tiles (host array) */
+} tadev_permute_source;
+int tadev_provider_permute(void* permute_source, tadev_stream s, int ntiles, const uint64_t* tokens,
+                           double* const* d_dst, const size_t* elems);
 
 typedef struct {
   int64_t nsteps, nsteps_skipped, npairs, nlaunches;
@@ -256,6 +289,7 @@ typedef struct {
   int32_t row_blocks; /* result row blocks used */
   int64_t h2d_bytes;  /* host->device bytes moved inside the call (host-resident operands) */
   int64_t d2h_bytes;  /* device->host bytes moved inside the call (host-resident result) */
+  int64_t lazy_tiles; /* tiles materialised by providers */
 } tadev_summa_stats;
 
 int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_stats* stats);

@@ -5,7 +5,12 @@ the public API on one GPU, timed with CUDA events, and spot-checked against the 
   C4r  CCSD PPL R(a,b,i,j)=T(c,d,i,j)*V(a,b,c,d), o=100 (64+36), v REDUCED to 256 (4x64):
        V at v=800 is 3.28 TB and does not fit in HBM; same code path, same tiling
   C5r  C(i,a,j,b)=A(i,k,a,c)*B(j,c,k,b), i=j=k REDUCED to 64 (tile 16), a=b=c=512 (tile 64)
-python scripts/bench_configs.py [C1,C3,C4r,C5r] [out.jsonl]"""
+  C4   the full config: o=100 v=800 tile=64. V (3.28 TB) is a LAZY array: its tiles are generated on
+       the device from the counter RNG when a SUMMA window needs them; the engine exchanges the
+       operands (R[ab,ij] = V[ab,cd] T[cd,ij], plain NN, no permutation) and walks R in row blocks
+  C5   the full config: i=j=k=128 (tile 16), a=b=c=512 (tile 64); argument permutations are
+       performed just in time per SUMMA window (no permuted copies: 3 x 34.4 GB stay resident)
+python scripts/bench_configs.py [C1,C3,C4r,C5r,C4,C5] [out.jsonl]"""
 import itertools
 import json
 import os
@@ -54,7 +59,7 @@ def spot_check(c, a, b, spec, seeds, ordinal):
     return O.rel_frobenius(c.find(ordinal), ref)
 
 
-def run(name, a, b, c, target, lidx, ridx, flops, seeds, reps=2, note=""):
+def run(name, a, b, c, target, lidx, ridx, flops, seeds, reps=2, note="", spot="middle"):
     best_total, st = 1e30, None
     for _ in range(reps):
         dev.sync()
@@ -65,10 +70,13 @@ def run(name, a, b, c, target, lidx, ridx, flops, seeds, reps=2, note=""):
         st = ContEngine.last_stats
         wall = time.perf_counter() - t0
     spec = f"{lidx.replace(',', '')},{ridx.replace(',', '')}->{target.replace(',', '')}"
-    o = sorted(c.tiles)[len(c.tiles) // 2]
+    o = sorted(c.tiles)[len(c.tiles) // 2] if spot == "middle" else sorted(c.tiles)[-1]
+    t0 = time.perf_counter()
     err = spot_check(c, a, b, spec, seeds, o)
+    spot_s = time.perf_counter() - t0
     rec = {"config": name, "note": note, "algorithmic_flop": flops, "executed_flop": st.flops, "npairs": st.npairs,
-           "gemm_launches": st.nlaunches, "gemm_ms": st.device_ms, "permute_ms": st.permute_ms, "total_ms": best_total,
+           "gemm_launches": st.nlaunches, "row_blocks": st.row_blocks, "lazy_tiles": st.lazy_tiles, "spot_check_s": spot_s,
+           "gemm_ms": st.device_ms, "permute_ms": st.permute_ms, "total_ms": best_total,
            "wall_s_last": wall, "tflops_effective": flops / (best_total * 1e-3) / 1e12,
            "tflops_gemm": st.flops / (st.device_ms * 1e-3) / 1e12, "fp64_peak_tflops": peak,
            "frac_of_peak_gemm": st.flops / (st.device_ms * 1e-3) / 1e12 / peak, "spot_rel_frobenius": err}
@@ -137,6 +145,31 @@ if "C4r" in which:
     run("C4r CCSD PPL o=100 v=256 tile=64", T2, V, R, "a,b,i,j", "c,d,i,j", "a,b,c,d", 2.0 * 100 ** 2 * 256 ** 4, (7, 8),
         note="v reduced from 800 (V would be 3.28 TB); opA=T, opB=T, result permute (i,j,a,b)->(a,b,i,j)")
     for x in (T2, V, R):
+        x.release()
+
+if "C4" in which:
+    o1 = TiledRange1(0, 64, 100)
+    v1 = TiledRange1.make_uniform(800, 64)
+    T2 = DistArray(world, TiledRange([v1, v1, o1, o1])).fill_random(7)
+    V = DistArray(world, TiledRange([v1, v1, v1, v1]), memory="lazy", lazy_seed=8)
+    R = DistArray(world, TiledRange([v1, v1, o1, o1]))
+    run("C4 CCSD PPL o=100 v=800 tile=64", T2, V, R, "a,b,i,j", "c,d,i,j", "a,b,c,d", 2.0 * 100 ** 2 * 800.0 ** 4, (7, 8), reps=1,
+        note="full size; V (3.28 TB) lazy: generated per tile on the device inside the timed region; operands exchanged "
+             "(NN, no permutation); R in row blocks", spot="last")
+    for x in (T2, V, R):
+        x.release()
+
+if "C5" in which:
+    s1 = TiledRange1.make_uniform(128, 16)
+    b1 = TiledRange1.make_uniform(512, 64)
+    A = DistArray(world, TiledRange([s1, s1, b1, b1])).fill_random(9)
+    B = DistArray(world, TiledRange([s1, b1, s1, b1])).fill_random(10)
+    Cc = DistArray(world, TiledRange([s1, b1, s1, b1]))
+    run("C5 permuted 4-index i=j=k=128 a=b=c=512 tiles 16/64", A, B, Cc, "i,a,j,b", "i,k,a,c", "j,c,k,b",
+        2.0 * (128.0 * 512) ** 3, (9, 10), reps=1,
+        note="full size; both operands explicitly permuted (general), just in time per SUMMA window (permute provider); "
+             "permute time is inside gemm_ms")
+    for x in (A, B, Cc):
         x.release()
 
 if "C5r" in which:

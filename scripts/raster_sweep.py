@@ -13,17 +13,14 @@ N = sys.argv[2] if len(sys.argv) > 2 else "16384"
 VARIANTS = [
     {"TADEV_RASTER_S": "0"},
     {"TADEV_RASTER_S": "12"},
-    {"TADEV_RASTER_S": "12", "TADEV_RASTER_ROWMAJOR": "1"},
-    {"TADEV_RASTER_S": "12", "TADEV_SCHED_STATIC": "1"},
-    {"TADEV_RASTER_S": "12", "TADEV_RASTER_ROWMAJOR": "1", "TADEV_SCHED_STATIC": "1"},
-    {"TADEV_RASTER_S": "0", "TADEV_SCHED_STATIC": "1"},
-    {"TADEV_RASTER_S": "12", "TADEV_TMAP_L2PROMO": "0"},
-    {"TADEV_RASTER_S": "12", "TADEV_RASTER_ROWMAJOR": "1", "TADEV_TMAP_L2PROMO": "2"},
-    {"TADEV_RASTER_S": "8"},
-    {"TADEV_RASTER_S": "16"},
-    {"TADEV_RASTER_S": "0", "TADEV_TMAP_L2PROMO": "0"},
-    {"TADEV_RASTER_S": "6", "TADEV_SCHED_STATIC": "1"},
+    {"TADEV_RASTER_S": "12", "TADEV_WAVE_SYNC": "1"},
+    {"TADEV_RASTER_S": "12", "TADEV_WAVE_SYNC": "4"},
+    {"TADEV_RASTER_S": "12", "TADEV_WAVE_SYNC": "16"},
+    {"TADEV_RASTER_S": "0", "TADEV_WAVE_SYNC": "4"},
+    {"TADEV_RASTER_S": "12", "TADEV_RASTER_ROWMAJOR": "1", "TADEV_WAVE_SYNC": "4"},
 ]
+if os.environ.get("RASTER_VARIANTS"):
+    VARIANTS = json.loads(os.environ["RASTER_VARIANTS"])
 results = []
 for v in VARIANTS:
     env = dict(os.environ)

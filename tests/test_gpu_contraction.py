@@ -78,9 +78,18 @@ def test_cont_ccsd_ppl_shape(world):
     ta_cc_abcd.cpp:240) — both operands matrix_transpose, result permute; ragged
     occupied/virtual tilings like o=100/64, v=800/64."""
     o, v = TiledRange1(0, 6, 10), TiledRange1(0, 8, 16, 20)
-    st = _check(world, "a,b,i,j", "c,d,i,j", "a,b,c,d", _tr(v, v, o, o), _tr(v, v, v, v), _tr(v, v, o, o))
-    assert st.permute_ms > 0.0  # the result permutation ran
-    _check(world, "a,b,i,j", "c,d,i,j", "a,b,c,d", _tr(v, v, o, o), _tr(v, v, v, v), _tr(v, v, o, o), integer=False, factor=0.5)
+    old = ContEngine.exchange_operands
+    try:
+        ContEngine.exchange_operands = False  # the reference's plan: opA = opB = T + result permutation
+        st = _check(world, "a,b,i,j", "c,d,i,j", "a,b,c,d", _tr(v, v, o, o), _tr(v, v, v, v), _tr(v, v, o, o))
+        assert st.permute_ms > 0.0  # the result permutation ran
+        _check(world, "a,b,i,j", "c,d,i,j", "a,b,c,d", _tr(v, v, o, o), _tr(v, v, v, v), _tr(v, v, o, o), integer=False, factor=0.5)
+        ContEngine.exchange_operands = True  # R[ab,ij] = V[ab,cd] T[cd,ij]: plain NN, no permutation at all
+        st = _check(world, "a,b,i,j", "c,d,i,j", "a,b,c,d", _tr(v, v, o, o), _tr(v, v, v, v), _tr(v, v, o, o))
+        assert st.permute_ms == 0.0
+        _check(world, "a,b,i,j", "c,d,i,j", "a,b,c,d", _tr(v, v, o, o), _tr(v, v, v, v), _tr(v, v, o, o), integer=False, factor=0.5)
+    finally:
+        ContEngine.exchange_operands = old
 
 
 def test_cont_general_permutes(world):
@@ -89,6 +98,64 @@ def test_cont_general_permutes(world):
     s, b = TiledRange1(0, 2, 6), TiledRange1(0, 4, 8, 10)
     _check(world, "i,a,j,b", "i,k,a,c", "j,c,k,b", _tr(s, s, b, b), _tr(s, b, s, b), _tr(s, b, s, b))
     _check(world, "i,a,j,b", "i,k,a,c", "j,c,k,b", _tr(s, s, b, b), _tr(s, b, s, b), _tr(s, b, s, b), integer=False)
+
+
+@pytest.mark.parametrize("spl,rb", [(0, 0), (1, 0), (2, 2), (1, 3)])
+def test_cont_streamed_permutes(world, spl, rb):
+    """Argument permutations performed just in time per SUMMA window by the permute provider (lazy
+    tiles, dist_eval/array_eval.h:42,170) instead of up front: same exact result, no permuted copy."""
+    s, b = TiledRange1(0, 2, 6), TiledRange1(0, 4, 8, 10)
+    old = (ContEngine.stream_permutes, ContEngine.steps_per_launch, ContEngine.row_blocks)
+    try:
+        ContEngine.stream_permutes, ContEngine.steps_per_launch, ContEngine.row_blocks = True, spl, rb
+        st = _check(world, "i,a,j,b", "i,k,a,c", "j,c,k,b", _tr(s, s, b, b), _tr(s, b, s, b), _tr(s, b, s, b))
+        assert st.lazy_tiles >= 2 * 2 * 2 * 3 * 3 and st.permute_ms == 0.0
+        _check(world, "a,i,b,j", "i,k,a,c", "j,c,k,b", _tr(s, s, b, b), _tr(s, b, s, b), _tr(b, s, b, s), integer=False)
+    finally:
+        ContEngine.stream_permutes, ContEngine.steps_per_launch, ContEngine.row_blocks = old
+
+
+@pytest.mark.parametrize("lazy_side", ["left", "right", "both"])
+def test_cont_lazy_operands(world, lazy_side):
+    """Operands that are never stored: tiles are generated on the device from the counter RNG when the
+    SUMMA window needs them (BASELINE config 4's V = 3.28 TB). Same values as the materialised array
+    (fill_random uses the same generator), checked against host-regenerated tiles too."""
+    from tests import util_rng
+    dm, dk, dn = TiledRange1(0, 4, 10, 16, 18), TiledRange1(0, 6, 8, 20), TiledRange1(0, 2, 12, 20, 24)
+    trL, trR, trC = _tr(dm, dk), _tr(dk, dn), _tr(dm, dn)
+
+    def make(tr, seed, lazy):
+        if lazy:
+            return DistArray(world, tr, memory="lazy", lazy_seed=seed)
+        return DistArray(world, tr).fill_random(seed)
+
+    def host(tr, seed):
+        full = np.zeros(tr.elements_shape)
+        for o in range(tr.ntiles):
+            idx = tr.tile_index(o)
+            ext = tr.tile_extent(idx)
+            full[tr.tile_slices(idx)] = util_rng.tile_fill(o, int(np.prod(ext)), seed).reshape(ext)
+        return full
+
+    a = make(trL, 11, lazy_side in ("left", "both"))
+    b = make(trR, 12, lazy_side in ("right", "both"))
+    ref = host(trL, 11) @ host(trR, 12)
+    c = DistArray(world, trC)
+    old = (ContEngine.steps_per_launch, ContEngine.row_blocks)
+    try:
+        for spl, rb in ((0, 0), (1, 2), (2, 4)):
+            ContEngine.steps_per_launch, ContEngine.row_blocks = spl, rb
+            c["m,n"] = a["m,k"] * b["k,n"]
+            assert O.rel_frobenius(c.to_numpy(), ref) < TOL, (spl, rb)
+            assert ContEngine.last_stats.lazy_tiles > 0
+        ContEngine.steps_per_launch, ContEngine.row_blocks = 0, 0
+        c["n,m"] = a["m,k"] * b["k,n"]  # exchanged operands: the lazy array changes sides
+        assert O.rel_frobenius(c.to_numpy(), ref.T) < TOL
+    finally:
+        ContEngine.steps_per_launch, ContEngine.row_blocks = old
+    assert O.rel_frobenius(a.find(1), host(trL, 11)[trL.tile_slices(trL.tile_index(1))]) < 1e-15
+    for x in (a, b, c):
+        x.release()
 
 
 def test_cont_rank3_and_outer_product(world):

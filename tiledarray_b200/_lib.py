@@ -53,16 +53,26 @@ class SummaPlanC(C.Structure):
                 ("threshold", C.c_float),
                 ("a_tiles", C.POINTER(C.c_void_p)), ("b_tiles", C.POINTER(C.c_void_p)), ("c_tiles", C.POINTER(C.c_void_p)),
                 ("accumulate", C.c_int32), ("depth", C.c_int32), ("steps_per_launch", C.c_int32),
-                ("flags", C.c_int32), ("row_blocks", C.c_int32), ("reserved", C.c_int32)]
+                ("flags", C.c_int32), ("row_blocks", C.c_int32), ("reserved", C.c_int32),
+                ("a_provider", C.c_void_p), ("a_user", C.c_void_p), ("b_provider", C.c_void_p), ("b_user", C.c_void_p)]
 
 
-SUMMA_A_ON_HOST, SUMMA_B_ON_HOST, SUMMA_C_ON_HOST = 1, 2, 4
+SUMMA_A_ON_HOST, SUMMA_B_ON_HOST, SUMMA_C_ON_HOST, SUMMA_A_LAZY, SUMMA_B_LAZY = 1, 2, 4, 8, 16
+
+
+class UniformSourceC(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("seed", C.c_uint64)]
+
+
+class PermuteSourceC(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("rank", C.c_int32), ("perm", C.c_int32 * 16),
+                ("extents", C.POINTER(C.c_int64)), ("src", C.POINTER(C.c_void_p))]
 
 
 class SummaStatsC(C.Structure):
     _fields_ = [("nsteps", C.c_int64), ("nsteps_skipped", C.c_int64), ("npairs", C.c_int64), ("nlaunches", C.c_int64),
                 ("flops", C.c_double), ("bcast_bytes", C.c_int64), ("device_ms", C.c_float), ("row_blocks", C.c_int32),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("lazy_tiles", C.c_int64)]
 
 
 # every exported symbol of include/tadev.h with its prototype (restype, argtypes)
@@ -111,6 +121,8 @@ PROTOTYPES = {
     "tadev_comm_destroy": (_i, [_vp]),
     "tadev_bcast_panel": (_i, [_vp, _vp, _i, _i, _vp, _sz]),
     "tadev_summa_f64": (_i, [_vp, _P(SummaPlanC), _P(SummaStatsC)]),
+    "tadev_provider_uniform": (_i, [_vp, _vp, _i, _P(_u64), _P(_vp), _P(_sz)]),
+    "tadev_provider_permute": (_i, [_vp, _vp, _i, _P(_u64), _P(_vp), _P(_sz)]),
     "tadev_summa_schedule": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _P(C.c_int32), _vp, _vp,
                                   _i64, _P(_i64)]),
     "tadev_summa_steps": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -125,7 +125,8 @@ template <int OPA, int OPB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngroups,
                            const WsTask* __restrict__ tasks, const int2* __restrict__ items,
-                           int total_tiles, int* __restrict__ tile_counter, double alpha, int static_sched) {
+                           int total_tiles, int* __restrict__ tile_counter, double alpha, int static_sched,
+                           int wave_sync) {
   constexpr bool A_KIN = (OPA == TADEV_OP_N);  // A stored [m][k]
   constexpr bool B_KIN = (OPB == TADEV_OP_T);  // B stored [n][k]
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -158,6 +159,19 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
         if (lane == 0) { ctrl->sched_group[slot] = -1; mbar_arrive(&ctrl->sched_full[slot]); }
         break;
       }
+      // Re-alignment: CTAs that share operand panels through L2 must stay within a few dozen k-slabs
+      // of each other (126 MB L2 vs 148 streams of 32 KB per slab); start-time jitter accumulates
+      // over hundreds of waves, so every `wave_sync` waves all CTAs wait for the previous wave.
+      if (wave_sync > 0) {
+        const int wave = w / (int)gridDim.x;
+        if (wave > 0 && wave % wave_sync == 0) {
+          const int need = wave * (int)gridDim.x;
+          if (lane == 0) {
+            while (*reinterpret_cast<volatile int*>(tile_counter + 1) < need) __nanosleep(200);
+          }
+          __syncwarp();
+        }
+      }
       // work item w of the rasterised order (host-built, see raster_items): group + 128x128 block
       const int2 item = __ldg(items + w);
       const int gi = item.x;
@@ -177,6 +191,7 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
         mbar_wait(&ctrl->empty[stage], phase ^ 1);
         if (lane == 0) { ctrl->kb[stage] = LAST_FLAG; mbar_arrive(&ctrl->full[stage]); }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (wave_sync > 0 && lane == 0) atomicAdd(tile_counter + 1, 1);
         continue;
       }
       for (int ti = grp.task_begin; ti <= last_task; ++ti) {
@@ -226,6 +241,7 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (wave_sync > 0 && lane == 0) atomicAdd(tile_counter + 1, 1);  // all loads of this item are issued
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
@@ -469,14 +485,14 @@ int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* group
 
 template <int OPA, int OPB>
 int launch_ws_variant(cudaStream_t s, int grid, const tadev_gemm_group* d_groups, int ngroups, const WsTask* d_tasks,
-                      const int2* d_items, int total_tiles, int* d_counter, double alpha, int static_sched) {
+                      const int2* d_items, int total_tiles, int* d_counter, double alpha, int static_sched, int wave_sync) {
   auto kern = gemm_grouped_f64_ws_kernel<OPA, OPB>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
     TADEV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, NTHREADS, SMEM_BYTES, s>>>(d_groups, ngroups, d_tasks, d_items, total_tiles, d_counter, alpha, static_sched);
+  kern<<<grid, NTHREADS, SMEM_BYTES, s>>>(d_groups, ngroups, d_tasks, d_items, total_tiles, d_counter, alpha, static_sched, wave_sync);
   TADEV_CHECK_CUDA(cudaGetLastError());
   return TADEV_OK;
 }
@@ -588,6 +604,22 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
   if (grid > total_cta_tiles) grid = total_cta_tiles;
   raster_items(h_groups, ngroups, grid, (int2*)((char*)h + off_p), total_cta_tiles);
   static const int static_sched = getenv("TADEV_SCHED_STATIC") ? atoi(getenv("TADEV_SCHED_STATIC")) : 0;
+  // wave re-alignment (see the kernel) pays off when all work items take the same time (dense
+  // contractions: every result tile has the same total K); with ragged K it would idle CTAs.
+  static const int wave_sync_env = getenv("TADEV_WAVE_SYNC") ? atoi(getenv("TADEV_WAVE_SYNC")) : -1;
+  int wave_sync = wave_sync_env;
+  if (wave_sync < 0) {
+    bool uniform = ngroups > 1;
+    int64_t k0 = -1;
+    for (int gi = 0; gi < ngroups && uniform; ++gi) {
+      if (h_groups[gi].m == 0 || h_groups[gi].n == 0) continue;
+      int64_t kk = 0;
+      for (int ti = h_groups[gi].task_begin; ti < h_groups[gi].task_end; ++ti) kk += h_tasks[ti].k;
+      if (k0 < 0) k0 = kk;
+      uniform = (kk == k0) && h_groups[gi].raster != 0;
+    }
+    wave_sync = uniform ? 1 : 0;
+  }
   memset((char*)h + off_c, 0, 16);
   TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, off_c + 16, cudaMemcpyHostToDevice, s));
   ctx->launches++;
@@ -596,10 +628,10 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
   const int2* dp = (const int2*)((char*)d + off_p);
   int* dc = (int*)((char*)d + off_c);
   switch ((opA << 1) | opB) {
-    case 0: rc = launch_ws_variant<0, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched); break;
-    case 1: rc = launch_ws_variant<0, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched); break;
-    case 2: rc = launch_ws_variant<1, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched); break;
-    case 3: rc = launch_ws_variant<1, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched); break;
+    case 0: rc = launch_ws_variant<0, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched, wave_sync); break;
+    case 1: rc = launch_ws_variant<0, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched, wave_sync); break;
+    case 2: rc = launch_ws_variant<1, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched, wave_sync); break;
+    case 3: rc = launch_ws_variant<1, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched, wave_sync); break;
     default: tadev_set_error("launch_gemm_grouped_f64_ws: bad op flags %d %d", opA, opB); rc = TADEV_EINVAL;
   }
   TADEV_CHECK_CUDA(cudaEventRecord(done, s));

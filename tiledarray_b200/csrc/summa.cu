@@ -83,6 +83,53 @@ extern "C" int tadev_bcast_panel(tadev_ctx* ctx, tadev_stream s, int which, int 
   return TADEV_OK;
 }
 
+// ---- built-in tile providers for lazy operands ---------------------------------------------------
+extern "C" int tadev_provider_uniform(void* user, tadev_stream s, int ntiles, const uint64_t* tokens,
+                                      double* const* d_dst, const size_t* elems) {
+  const tadev_uniform_source* src = static_cast<const tadev_uniform_source*>(user);
+  TADEV_REQUIRE(src && src->ctx && (ntiles == 0 || (tokens && d_dst && elems)), "tadev_provider_uniform: null");
+  for (int n = 0; n < ntiles; ++n) {
+    TADEV_REQUIRE(tokens[n] != 0, "tadev_provider_uniform: zero token");
+    int rc = tadev_fill_uniform_f64(src->ctx, s, d_dst[n], elems[n], src->seed, (tokens[n] - 1) << 32);
+    if (rc) return rc;
+  }
+  return TADEV_OK;
+}
+
+// Argument-tile permutation performed when the SUMMA window needs the tile (ArrayEvalImpl /
+// LazyArrayTile with a permuting op, dist_eval/array_eval.h:42,170): tiles with identical extents
+// share one batched launch.
+extern "C" int tadev_provider_permute(void* user, tadev_stream s, int ntiles, const uint64_t* tokens,
+                                      double* const* d_dst, const size_t* elems) {
+  const tadev_permute_source* src = static_cast<const tadev_permute_source*>(user);
+  TADEV_REQUIRE(src && src->ctx && src->extents && src->src && src->rank >= 0 && src->rank <= 16, "tadev_provider_permute: bad source");
+  TADEV_REQUIRE(ntiles == 0 || (tokens && d_dst && elems), "tadev_provider_permute: null");
+  const int R = src->rank;
+  std::vector<char> done((size_t)ntiles, 0);
+  std::vector<const void*> ins;
+  std::vector<void*> outs;
+  for (int n = 0; n < ntiles; ++n) {
+    if (done[n]) continue;
+    TADEV_REQUIRE(tokens[n] != 0, "tadev_provider_permute: zero token");
+    const int64_t* ext = src->extents + (size_t)(tokens[n] - 1) * R;
+    ins.clear(); outs.clear();
+    for (int q = n; q < ntiles; ++q) {
+      if (done[q] || tokens[q] == 0) continue;
+      const int64_t* eq = src->extents + (size_t)(tokens[q] - 1) * R;
+      if (q != n && memcmp(eq, ext, sizeof(int64_t) * R) != 0) continue;
+      size_t vol = 1;
+      for (int d = 0; d < R; ++d) vol *= (size_t)eq[d];
+      TADEV_REQUIRE(vol == elems[q], "tadev_provider_permute: tile %d has %zu elements, the driver expects %zu", q, vol, elems[q]);
+      ins.push_back(src->src[tokens[q] - 1]);
+      outs.push_back(d_dst[q]);
+      done[q] = 1;
+    }
+    int rc = tadev_permute_batched(src->ctx, s, R, ext, src->perm, 8, (int)ins.size(), ins.data(), outs.data());
+    if (rc) return rc;
+  }
+  return TADEV_OK;
+}
+
 namespace {
 
 inline size_t pad2(size_t n) { return (n + 1) & ~size_t(1); }  // keep every tile 16-byte aligned
@@ -124,6 +171,12 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   const int Mt = P.Mt, Nt = P.Nt, Kt = P.Kt;
   const bool a_host = (P.flags & TADEV_SUMMA_A_ON_HOST) != 0, b_host = (P.flags & TADEV_SUMMA_B_ON_HOST) != 0,
              c_host = (P.flags & TADEV_SUMMA_C_ON_HOST) != 0;
+  const bool a_lazy = (P.flags & TADEV_SUMMA_A_LAZY) != 0, b_lazy = (P.flags & TADEV_SUMMA_B_LAZY) != 0;
+  TADEV_REQUIRE(!(a_lazy && a_host) && !(b_lazy && b_host), "tadev_summa_f64: an operand cannot be both lazy and host-resident");
+  TADEV_REQUIRE((!a_lazy || P.a_provider) && (!b_lazy || P.b_provider), "tadev_summa_f64: lazy operand without a tile provider");
+  // "staged" operands have no device-resident tiles: every panel is materialised in the ring (or the
+  // B cache) by an upload or by the provider, on the staging stream
+  const bool a_stg = a_host || a_lazy, b_stg = b_host || b_lazy;
   TADEV_CHECK_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s0 = ctx->streams[0];                       // compute
   cudaStream_t sd = ctx->streams[ctx->streams.size() > 1 ? 1 : 0];  // result download
@@ -137,6 +190,19 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   std::vector<int> my_rows;
   for (int i = r; i < Mt; i += Pr) my_rows.push_back(i);
   int nb = 1;
+  if (!c_host && (P.row_blocks > 0 || a_lazy)) {
+    // device-resident result in row blocks: bounds the A panel of one step when A is generated on
+    // the fly (each block needs only its own rows of the panel). Same count on every rank.
+    const int max_rows = (Mt + Pr - 1) / Pr;
+    nb = P.row_blocks;
+    if (nb <= 0) {
+      double panel = 0, kmax = 0;
+      for (int k = 0; k < Kt; ++k) kmax = std::max(kmax, (double)P.k_ext[k]);
+      for (int rr = 0; rr < Pr; ++rr) { double t = 0; for (int i = rr; i < Mt; i += Pr) t += (double)P.m_ext[i]; panel = std::max(panel, t * kmax * 8.0); }
+      nb = (int)std::ceil(panel / (2.0 * 1073741824.0));
+    }
+    nb = std::max(1, std::min(nb, max_rows));
+  }
   if (c_host) {
     const int max_rows = (Mt + Pr - 1) / Pr;
     double m_sum = 0, n_sum = 0;
@@ -149,7 +215,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   }
   // B staged through the device (received by broadcast or uploaded from the host) is kept for all
   // row blocks when it fits the cache budget; the dense upper bound is the same on every rank.
-  const bool b_staged = b_host || (multi && Pr > 1);
+  const bool b_staged = b_stg || (multi && Pr > 1);
   bool b_cache = false;
   if (nb > 1 && b_staged) {
     double k_sum = 0, n_max = 0;
@@ -162,7 +228,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
 
   int W = P.steps_per_launch;
   if (W <= 0) {
-    if (!multi && !a_host && !b_host) W = std::max(1, Kt);
+    if (!multi && !a_stg && !b_stg) W = std::max(1, Kt);
     else {
       double avgk = 0;
       for (int k = 0; k < Kt; ++k) avgk += (double)P.k_ext[k];
@@ -170,7 +236,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
       W = (int)std::min<double>(64.0, std::max(1.0, std::ceil(4096.0 / std::max(1.0, avgk))));
     }
   }
-  const size_t kMaxWindowBytes = size_t(3) << 30;
+  const size_t kMaxWindowBytes = size_t(5) << 30;
   const int D = std::max(2, P.depth > 0 ? P.depth : 2);
 
   // ---- per-block step views and windows
@@ -185,7 +251,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     size_t e = 0;
     for (int j : S.steps[si].b_cols) e += pad2(tile_b_elems(S.steps[si].k, j));
     b_cache_off[si] = b_cache_elems;
-    if (b_cache && (S.steps[si].bcast_b || b_host)) b_cache_elems += e;
+    if (b_cache && (S.steps[si].bcast_b || b_stg)) b_cache_elems += e;
   }
   for (int b = 0; b < nb; ++b) {
     const int L = (int)my_rows.size();
@@ -213,9 +279,9 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     for (int x = 0; x < (int)bsteps[b].size(); ++x) {
       const BlockStep& bs = bsteps[b][x];
       size_t need = 0;
-      if (bs.bcast_a || (a_host && bs.compute)) need += bs.a_elems * 8;
-      const bool b_to_cache = b_cache && (bs.st->bcast_b || b_host);
-      if (!b_to_cache && (bs.bcast_b || (b_host && bs.compute))) need += bs.b_elems * 8;
+      if (bs.bcast_a || (a_stg && bs.compute)) need += bs.a_elems * 8;
+      const bool b_to_cache = b_cache && (bs.st->bcast_b || b_stg);
+      if (!b_to_cache && (bs.bcast_b || (b_stg && bs.compute))) need += bs.b_elems * 8;
       // the very first window is a single step so that the pipeline fills quickly
       const int wcap = (b == 0 && bwins[b].empty()) ? 1 : W;
       if (!cur.steps.empty() && (ncomp >= wcap || cur.bytes + need > kMaxWindowBytes)) {
@@ -227,7 +293,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     if (!cur.steps.empty()) bwins[b].push_back(std::move(cur));
     for (auto& w : bwins[b]) max_bytes = std::max(max_bytes, w.bytes);
   }
-  if (!multi && !a_host && !b_host) {  // P == 1, device-resident: undo the short first window
+  if (!multi && !a_stg && !b_stg) {  // P == 1, device-resident: undo the short first window
     // (no staging at all, so one launch for everything is best)
     for (int b = 0; b < nb; ++b) {
       Window all;
@@ -314,7 +380,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     marks.push_back({what, blk, win, e});
   };
   std::vector<char> touched((size_t)Mt * Nt, 0);
-  int64_t npairs = 0, nlaunches = 0, bcast_bytes = 0, h2d_bytes = 0, d2h_bytes = 0;
+  int64_t npairs = 0, nlaunches = 0, bcast_bytes = 0, h2d_bytes = 0, d2h_bytes = 0, lazy_tiles = 0;
   double flops = 0.0;
   struct Contribution { int64_t key; const double* A; const double* B; int k; };
   std::vector<Contribution> contrib;
@@ -327,16 +393,32 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   // Stage one panel: returns device pointers of its tiles. `mine` = I own the source tiles.
   // host-resident sources are uploaded (sh), device-resident ones are used in place when they need
   // no transport, broadcast in place when contiguous, or packed (sc).
-  auto stage_panel = [&](bool on_host, bool needs_bcast, bool mine, const std::vector<const double*>& src,
-                         const std::vector<size_t>& elems, double* dest, bool* used_dest, bool* did_h2d,
-                         std::vector<const double*>& out) -> int {
+  std::vector<uint64_t> prov_tok;
+  std::vector<double*> prov_dst;
+  auto stage_panel = [&](bool on_host, tadev_tile_provider provider, void* user, bool needs_bcast, bool mine,
+                         const std::vector<const double*>& src, const std::vector<size_t>& elems, double* dest,
+                         bool* used_dest, bool* did_h2d, std::vector<const double*>& out) -> int {
     out.assign(src.size(), nullptr);
     *used_dest = false;
-    if (!needs_bcast && !on_host) { for (size_t n = 0; n < src.size(); ++n) out[n] = src[n]; return TADEV_OK; }
+    if (!needs_bcast && !on_host && !provider) { for (size_t n = 0; n < src.size(); ++n) out[n] = src[n]; return TADEV_OK; }
     double* panel = dest;
     bool inplace = false;
     if (mine) {
-      if (on_host) {
+      if (provider) {  // lazy tiles: src[] holds opaque tokens; the provider fills the panel on the staging stream
+        prov_tok.clear(); prov_dst.clear();
+        size_t o = 0;
+        for (size_t n = 0; n < src.size(); ++n) {
+          prov_tok.push_back((uint64_t)reinterpret_cast<uintptr_t>(src[n]));
+          prov_dst.push_back(panel + o);
+          o += pad2(elems[n]);
+        }
+        if (!src.empty()) {
+          int rc = provider(user, (tadev_stream)sh, (int)src.size(), prov_tok.data(), prov_dst.data(), elems.data());
+          if (rc) return rc;
+          lazy_tiles += (int64_t)src.size();
+        }
+        *did_h2d = true;
+      } else if (on_host) {
         size_t o = 0;
         for (size_t n = 0; n < src.size(); ++n) {
           TADEV_CHECK_CUDA(cudaMemcpyAsync(panel + o, src[n], elems[n] * 8, cudaMemcpyHostToDevice, sh));
@@ -419,7 +501,8 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
             src.push_back(tp); el.push_back(tile_a_elems(i, k));
           }
           bool used = false;
-          int rc = stage_panel(a_host, bs.bcast_a, mine, src, el, buf ? buf + cursor : nullptr, &used, &any_h2d, a_ptrs[wsi]);
+          int rc = stage_panel(a_host, a_lazy ? P.a_provider : nullptr, P.a_user, bs.bcast_a, mine, src, el,
+                               buf ? buf + cursor : nullptr, &used, &any_h2d, a_ptrs[wsi]);
           if (rc) return rc;
           if (used) { cursor += bs.a_elems; ring_touched = true; }
           if (bs.bcast_a) {
@@ -430,7 +513,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
         }
         // ---- B panel (travels along my grid column; root row k % Pr); cached across row blocks
         if (bs.bcast_b || bs.compute) {
-          const bool to_cache = b_cache && (st.bcast_b || b_host);
+          const bool to_cache = b_cache && (st.bcast_b || b_stg);
           if (to_cache && b_cached[si]) {
             size_t o = 0;
             b_ptrs[wsi].clear();
@@ -445,7 +528,8 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
             }
             double* dest = to_cache ? bcache + b_cache_off[si] : (buf ? buf + cursor : nullptr);
             bool used = false;
-            int rc = stage_panel(b_host, bs.bcast_b, mine, src, el, dest, &used, &any_h2d, b_ptrs[wsi]);
+            int rc = stage_panel(b_host, b_lazy ? P.b_provider : nullptr, P.b_user, bs.bcast_b, mine, src, el, dest, &used,
+                                 &any_h2d, b_ptrs[wsi]);
             if (rc) return rc;
             if (used && !to_cache) { cursor += bs.b_elems; ring_touched = true; }
             if (to_cache) {
@@ -593,6 +677,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     stats->h2d_bytes = h2d_bytes;
     stats->d2h_bytes = d2h_bytes;
     stats->row_blocks = nb;
+    stats->lazy_tiles = lazy_tiles;
   }
   cudaEventDestroy(ev_start); cudaEventDestroy(ev_end); cudaEventDestroy(ev_aux);
   for (int d = 0; d < D; ++d) { cudaEventDestroy(panel_ready[d]); cudaEventDestroy(buf_free[d]); cudaEventDestroy(h2d_done[d]); }

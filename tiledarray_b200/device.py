@@ -201,6 +201,18 @@ class Device:
         outs = (C.c_void_p * max(n, 1))(*[b.ptr for b in dsts])
         check(self.lib.tadev_permute_batched(self.ctx, stream or self.stream, rank, ext, pm, elem_bytes, n, ins, outs))
 
+    def permute_batched_ptrs(self, extent: Sequence[int], perm: Sequence[int], elem_bytes: int, src_ptrs: np.ndarray,
+                             dst_ptrs: np.ndarray, stream=None) -> None:
+        """tadev_permute_batched on arrays of raw device pointers (uint64)."""
+        rank, n = len(extent), len(src_ptrs)
+        ext = (C.c_int64 * max(rank, 1))(*extent)
+        pm = (C.c_int32 * max(rank, 1))(*perm)
+        ins = np.ascontiguousarray(src_ptrs, dtype=np.uint64)
+        outs = np.ascontiguousarray(dst_ptrs, dtype=np.uint64)
+        vpp = C.POINTER(C.c_void_p)
+        check(self.lib.tadev_permute_batched(self.ctx, stream or self.stream, rank, ext, pm, elem_bytes, n,
+                                             ins.ctypes.data_as(vpp), outs.ctypes.data_as(vpp)))
+
     def add_to(self, n: int, result: DeviceBuffer, arg: DeviceBuffer, stream=None) -> None:
         check(self.lib.tadev_add_to_f64(self.ctx, stream or self.stream, n, result.ptr, arg.ptr))
 

@@ -294,11 +294,17 @@ class DistArray:
     """
 
     def __init__(self, world: World, trange: TiledRange, shape: Optional[SparseShape] = None,
-                 owner=None, arena_order: Optional[Sequence[int]] = None, memory: str = "device"):
-        _ta_assert(memory in ("device", "host"), "DistArray: memory must be 'device' or 'host'")
+                 owner=None, arena_order: Optional[Sequence[int]] = None, memory: str = "device",
+                 lazy_seed: Optional[int] = None):
+        _ta_assert(memory in ("device", "host", "lazy"), "DistArray: memory must be 'device', 'host' or 'lazy'")
+        _ta_assert((memory == "lazy") == (lazy_seed is not None), "DistArray: memory='lazy' needs lazy_seed (and only it)")
         self.world, self.trange = world, trange
         self.memory = memory  # "host": tiles live in pinned host memory (TiledArray's default home for
-        #                       arrays) and are streamed through the GPU by the SUMMA driver
+        #                       arrays) and are streamed through the GPU by the SUMMA driver.
+        #                       "lazy": tiles are never stored; they are generated on the device when a
+        #                       contraction needs them (TiledArray's lazy tiles, array_eval.h:42) from the
+        #                       counter RNG keyed by (lazy_seed, tile ordinal) -- tensors larger than HBM.
+        self.lazy_seed = lazy_seed
         self.shape = shape if shape is not None else DenseShape()
         self._owner = owner or (lambda ordinal: 0)
         self.tiles: Dict[int, DeviceBuffer] = {}
@@ -319,7 +325,7 @@ class DistArray:
         return int(np.prod(self.trange.tile_extent(self.trange.tile_index(ordinal)), dtype=np.int64))
 
     def _allocate(self) -> None:
-        if self._arena is not None or self.tiles:
+        if self._arena is not None or self.tiles or self.memory == "lazy":
             return
         ords = self.local_nonzero_ordinals()
         if self._arena_order is not None:
@@ -350,6 +356,7 @@ class DistArray:
     def fill_random(self, seed: int) -> "DistArray":
         """uniform(-1,1) generated on the device; element value depends only on (seed, tile
         ordinal, offset in tile) so any distribution of the array holds identical data."""
+        _ta_assert(self.memory != "lazy", "fill_random: a lazy array is defined by its lazy_seed")
         self._allocate()
         dev = self.world.dev
         if self.memory == "host":  # generate on the device (one RNG implementation), park on the host
@@ -386,8 +393,16 @@ class DistArray:
 
     def find(self, ordinal: int) -> np.ndarray:
         """Local tile as a host array (dist_array.h:717)."""
-        _ta_assert(ordinal in self.tiles, "DistArray::find: tile is zero or not local")
         ext = self.trange.tile_extent(self.trange.tile_index(ordinal))
+        if self.memory == "lazy":  # materialise this one tile
+            _ta_assert(self.is_local(ordinal) and not self.is_zero(ordinal), "DistArray::find: tile is zero or not local")
+            n = self.tile_elems(ordinal)
+            tmp = self.world.dev.alloc(n * 8)
+            self.world.dev.fill_uniform(tmp, n, self.lazy_seed, ordinal << 32)
+            out = self.world.dev.download(tmp, np.float64, ext)
+            tmp.free()
+            return out
+        _ta_assert(ordinal in self.tiles, "DistArray::find: tile is zero or not local")
         if self.memory == "host":
             return self.tiles[ordinal].numpy(np.float64, ext).copy()
         return self.world.dev.download(self.tiles[ordinal], np.float64, ext)
@@ -473,6 +488,18 @@ class ContractionStats:
     h2d_bytes: int = 0
     d2h_bytes: int = 0
     row_blocks: int = 1
+    lazy_tiles: int = 0
+
+
+class _OperandView:
+    def __init__(self):
+        self.trange = self.shape = None
+        self.ords = np.zeros(0, dtype=np.int64)    # ordinals in the (permuted) tile grid
+        self.vals = np.zeros(0, dtype=np.uint64)   # device/host pointers, or provider tokens
+        self.provider = None                        # address of a tadev_tile_provider (lazy operand)
+        self.user = None                            # its user struct (kept alive here)
+        self.keep: list = []
+        self.tmp: list = []                         # device buffers to free after the contraction
 
 
 class ContEngine:
@@ -487,6 +514,8 @@ class ContEngine:
     steps_per_launch = 0  # K steps fused into one grouped-GEMM launch (0 = auto)
     row_blocks = 0        # result row blocks for host-resident results (0 = auto)
     exchange_operands = True  # evaluate C^T = B^T A^T when that needs fewer explicit tile permutations
+    stream_permutes = "auto"  # True/False/"auto": permute argument tiles just in time per SUMMA window
+    stream_permute_bytes = 8 << 30  # "auto": stream when the permuted copy would exceed this many bytes
 
     def __init__(self, result: TsrExpr, left: TsrExpr, right: TsrExpr, factor: float):
         self.result, self.left, self.right, self.factor = result, left, right, factor
@@ -507,37 +536,71 @@ class ContEngine:
     def _perm(arr, rank: int) -> Optional[List[int]]:
         return None if arr[0] < 0 else [int(x) for x in arr[:rank]]
 
-    def _permuted_operand(self, arr: DistArray, perm: Optional[List[int]]):
-        """Explicit argument permutation (ArrayEvalImpl/LazyArrayTile + UnaryWrapper<Noop>,
-        dist_eval/array_eval.h:42,170): returns (trange, shape, {ordinal: buffer}, temp buffers)."""
+    def _operand_view(self, arr: DistArray, perm: Optional[List[int]]) -> "_OperandView":
+        """The operand as the SUMMA driver sees it: permuted trange/shape plus, per local non-zero tile,
+        its ordinal in the permuted tile grid and either a pointer (device / pinned host) or a provider
+        token. Explicit argument permutations (ArrayEvalImpl/LazyArrayTile + UnaryWrapper<Noop>,
+        dist_eval/array_eval.h:42,170) are either materialised up front into one arena (one batched launch
+        per distinct tile extent) or, for big operands, performed just in time per SUMMA window by the
+        permute provider (no permuted copy in HBM)."""
+        v = _OperandView()
+        dev = self.dev
+        if arr.memory == "lazy":
+            _ta_assert(perm is None, "a lazy operand that needs an explicit permutation is not supported")
+            ords = np.asarray(arr.local_nonzero_ordinals(), dtype=np.int64)
+            v.trange, v.shape, v.ords, v.vals = arr.trange, arr.shape, ords, (ords + 1).astype(np.uint64)
+            v.user = _lib.UniformSourceC(dev.ctx.value, arr.lazy_seed)
+            v.provider = C.cast(dev.lib.tadev_provider_uniform, C.c_void_p).value
+            return v
+        ords = np.fromiter(arr.tiles.keys(), dtype=np.int64, count=len(arr.tiles))
+        ptrs = np.fromiter((b_.ptr for b_ in arr.tiles.values()), dtype=np.uint64, count=len(arr.tiles))
         if perm is None:
-            return arr.trange, arr.shape, arr.tiles, []
-        dims = [None] * len(perm)
+            v.trange, v.shape, v.ords, v.vals = arr.trange, arr.shape, ords, ptrs
+            return v
+        rank = len(perm)
+        dims = [None] * rank
         for i, p in enumerate(perm):
             dims[p] = arr.trange.dims[i]
-        tr = TiledRange(dims)
-        shape = arr.shape.perm(perm) if not arr.shape.is_dense() else arr.shape
-        # one arena for all permuted tiles; one batched launch per distinct tile extent
-        tiles: Dict[int, DeviceBuffer] = {}
-        sizes = {o: (buf.nbytes // 8 + 1) & ~1 for o, buf in arr.tiles.items()}
-        arena = self.dev.alloc(max(sum(sizes.values()), 2) * 8)
-        by_extent: Dict[Tuple[int, ...], Tuple[list, list]] = {}
-        off = 0
-        for o, buf in arr.tiles.items():
-            idx = arr.trange.tile_index(o)
-            ext = arr.trange.tile_extent(idx)
-            pidx = [0] * len(perm)
+        v.trange = TiledRange(dims)
+        v.shape = arr.shape.perm(perm) if not arr.shape.is_dense() else arr.shape
+        # vectorised index arithmetic: tile index, extent and permuted ordinal of every local tile
+        tshape = arr.trange.tiles_shape
+        idx = np.stack(np.unravel_index(ords, tshape), axis=1) if len(ords) else np.zeros((0, rank), dtype=np.int64)
+        ext = np.stack([np.asarray(d.extents, dtype=np.int64)[idx[:, a]] for a, d in enumerate(arr.trange.dims)], axis=1) \
+            if len(ords) else np.zeros((0, rank), dtype=np.int64)
+        pidx = np.empty_like(idx)
+        pidx[:, perm] = idx
+        v.ords = np.ravel_multi_index(tuple(pidx.T), v.trange.tiles_shape).astype(np.int64) if len(ords) else ords
+        nbytes = int(ext.prod(axis=1).sum()) * 8 if len(ords) else 0
+        stream = ContEngine.stream_permutes
+        if stream == "auto":
+            stream = nbytes > ContEngine.stream_permute_bytes
+        if stream:
+            v.vals = np.arange(1, len(ords) + 1, dtype=np.uint64)
+            v.keep = [np.ascontiguousarray(ext), np.ascontiguousarray(ptrs)]
+            src = _lib.PermuteSourceC()
+            src.ctx, src.rank = dev.ctx.value, rank
             for i, p in enumerate(perm):
-                pidx[p] = idx[i]
-            dst = arena.view(off * 8, buf.nbytes)
-            off += sizes[o]
-            srcs, dsts = by_extent.setdefault(tuple(ext), ([], []))
-            srcs.append(buf)
-            dsts.append(dst)
-            tiles[tr.tile_ordinal(pidx)] = dst
-        for ext, (srcs, dsts) in by_extent.items():
-            self.dev.permute_batched(ext, perm, 8, srcs, dsts)
-        return tr, shape, tiles, [arena]
+                src.perm[i] = p
+            src.extents = v.keep[0].ctypes.data_as(C.POINTER(C.c_int64))
+            src.src = v.keep[1].ctypes.data_as(C.POINTER(C.c_void_p))
+            v.user = src
+            v.provider = C.cast(dev.lib.tadev_provider_permute, C.c_void_p).value
+            return v
+        elems = ext.prod(axis=1) if len(ords) else np.zeros(0, dtype=np.int64)
+        padded = (elems + 1) & ~1
+        offs = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
+        arena = dev.alloc(max(int(offs[-1]), 2) * 8)
+        v.vals = (arena.ptr + offs[:-1] * 8).astype(np.uint64)
+        v.tmp = [arena]
+        # one batched launch per distinct tile extent
+        if len(ords):
+            uniq, inv = np.unique(ext, axis=0, return_inverse=True)
+            inv = inv.ravel()
+            for u in range(len(uniq)):
+                sel = np.nonzero(inv == u)[0]
+                dev.permute_batched_ptrs(tuple(int(x) for x in uniq[u]), perm, 8, ptrs[sel], v.vals[sel])
+        return v
 
     def eval(self) -> ContractionStats:
         P, w, dev = self.plan, self.world, self.dev
@@ -551,12 +614,15 @@ class ContEngine:
             Cres.release()  # hand the old result's memory back to the pool BEFORE allocating the new one
         nc = P.inner_rank
         stats = ContractionStats()
-        _ta_assert(A.memory == "device" or P.perm_left[0] < 0, "host-resident left operand needs an explicit permutation: not supported")
-        _ta_assert(B.memory == "device" or P.perm_right[0] < 0, "host-resident right operand needs an explicit permutation: not supported")
+        _ta_assert(A.memory != "host" or P.perm_left[0] < 0, "host-resident left operand needs an explicit permutation: not supported")
+        _ta_assert(B.memory != "host" or P.perm_right[0] < 0, "host-resident right operand needs an explicit permutation: not supported")
         _ta_assert(Cres.memory == "device" or P.perm_result[0] < 0, "host-resident result needs a result permutation: not supported")
+        _ta_assert(Cres.memory != "lazy", "the result of a contraction cannot be a lazy array")
         with dev.timer() as tperm:
-            trA, shA, tilesA, tmpA = self._permuted_operand(A, self._perm(P.perm_left, P.left_rank))
-            trB, shB, tilesB, tmpB = self._permuted_operand(B, self._perm(P.perm_right, P.right_rank))
+            vA = self._operand_view(A, self._perm(P.perm_left, P.left_rank))
+            vB = self._operand_view(B, self._perm(P.perm_right, P.right_rank))
+        trA, shA, trB, shB = vA.trange, vA.shape, vB.trange, vB.shape
+        tmpA, tmpB = vA.tmp, vB.tmp
         stats.permute_ms = tperm.ms if (tmpA or tmpB) else 0.0
 
         # fused (matrix) views: outer/inner mode ranges of each operand (GemmHelper, gemm_helper.h:62-98)
@@ -622,14 +688,12 @@ class ContEngine:
         a_tab = np.zeros(max(Mt * Kt, 1), dtype=np.uint64)
         b_tab = np.zeros(max(Kt * Nt, 1), dtype=np.uint64)
         c_tab = np.zeros(max(Mt * Nt, 1), dtype=np.uint64)
-        if tilesA:
-            oa = np.fromiter(tilesA.keys(), dtype=np.int64, count=len(tilesA))
-            pa = np.fromiter((b_.ptr for b_ in tilesA.values()), dtype=np.uint64, count=len(tilesA))
-            a_tab[oa if P.opA == _lib.OP_N else (oa % Mt) * Kt + oa // Mt] = pa
-        if tilesB:
-            ob = np.fromiter(tilesB.keys(), dtype=np.int64, count=len(tilesB))
-            pb = np.fromiter((b_.ptr for b_ in tilesB.values()), dtype=np.uint64, count=len(tilesB))
-            b_tab[ob if P.opB == _lib.OP_N else (ob % Kt) * Nt + ob // Kt] = pb
+        if len(vA.ords):
+            oa = vA.ords
+            a_tab[oa if P.opA == _lib.OP_N else (oa % Mt) * Kt + oa // Mt] = vA.vals
+        if len(vB.ords):
+            ob = vB.ords
+            b_tab[ob if P.opB == _lib.OP_N else (ob % Kt) * Nt + ob // Kt] = vB.vals
         # result tiles in GEMM order, owned cyclically by (i % Pr, j % Pc)
         # (vectorised: block-sparse results have 10^4 tiles and this is on the timed path)
         if r >= 0:
@@ -680,13 +744,19 @@ class ContEngine:
                                               c_tab.ctypes.data_as(vpp))
         sp.accumulate, sp.depth, sp.steps_per_launch = 0, ContEngine.depth, ContEngine.steps_per_launch
         sp.flags = ((_lib.SUMMA_A_ON_HOST if A.memory == "host" else 0) | (_lib.SUMMA_B_ON_HOST if B.memory == "host" else 0) |
-                    (_lib.SUMMA_C_ON_HOST if c_on_host else 0))
+                    (_lib.SUMMA_C_ON_HOST if c_on_host else 0) | (_lib.SUMMA_A_LAZY if vA.provider else 0) |
+                    (_lib.SUMMA_B_LAZY if vB.provider else 0))
+        if vA.provider:
+            sp.a_provider, sp.a_user = vA.provider, C.cast(C.pointer(vA.user), C.c_void_p)
+        if vB.provider:
+            sp.b_provider, sp.b_user = vB.provider, C.cast(C.pointer(vB.user), C.c_void_p)
         sp.row_blocks = ContEngine.row_blocks
         st = SummaStatsC()
         check(w.lib.tadev_summa_f64(dev.ctx, C.byref(sp), C.byref(st)))
         stats.nsteps, stats.nsteps_skipped, stats.npairs = st.nsteps, st.nsteps_skipped, st.npairs
         stats.nlaunches, stats.flops, stats.bcast_bytes, stats.device_ms = st.nlaunches, st.flops, st.bcast_bytes, st.device_ms
         stats.h2d_bytes, stats.d2h_bytes, stats.row_blocks = st.h2d_bytes, st.d2h_bytes, st.row_blocks
+        stats.lazy_tiles = st.lazy_tiles
         for b in tmpA + tmpB:
             b.free()
 
