@@ -294,6 +294,69 @@ typedef struct {
 
 int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_stats* stats);
 
+/* ---- the contraction engine ------------------------------------------------------------------
+ * replaces the expression-layer half of the path: ContEngine::perm_indices / init_struct /
+ * init_distribution / make_dist_eval (expressions/cont_engine.h:176-677) and the argument / result
+ * tile permutations around Summa (dist_eval/array_eval.h:42,170; contract_reduce.h:370-378).
+ * The caller describes the two argument arrays; `create` plans the contraction (optionally
+ * exchanging the operands), derives the result tiling, screens the result shape on the device and
+ * lays out the local result tiles; `eval` runs it into a caller-provided arena. This is what a
+ * TA::DistArray-level binding calls for `c("i,j") = a("i,k") * b("k,j")` (include/tiledarray.hpp,
+ * tiledarray_b200/tiledarray.py). */
+#define TADEV_MEM_DEVICE 0
+#define TADEV_MEM_HOST 1 /* pinned host memory; streamed through the GPU by the SUMMA driver */
+#define TADEV_MEM_LAZY 2 /* never stored: tiles generated on the device when needed (tadev_uniform_source) */
+typedef struct {
+  int32_t rank;
+  int32_t memory;            /* TADEV_MEM_* */
+  const int64_t* bounds;     /* tile boundaries, dimension after dimension: ntiles[d] + 1 entries each */
+  const int32_t* ntiles;     /* [rank] */
+  const float* norms;        /* SparseShape data (scaled norms, row-major over the tile grid); NULL = dense */
+  const void* const* tiles;  /* [prod ntiles] tile pointers; NULL entry = zero or not local. Lazy arrays: NULL
+                                table = every non-zero tile is local, else non-NULL entries mark local tiles */
+  uint64_t lazy_seed;
+} tadev_array_desc;
+
+typedef struct {
+  int32_t exchange_operands;    /* 1: may evaluate C^T = B^T A^T (tadev_plan_contraction_opt) */
+  int32_t stream_permutes;      /* 1 / 0 / -1 (auto): permute argument tiles per SUMMA window */
+  int64_t stream_permute_bytes; /* auto: stream when the permuted copy would exceed this size */
+  int32_t depth, steps_per_launch, row_blocks; /* forwarded to the SUMMA plan (0 = auto) */
+  float threshold;              /* SparseShape threshold */
+} tadev_contract_options;
+int tadev_contract_options_default(tadev_contract_options* o);
+
+typedef struct tadev_contraction tadev_contraction;
+typedef struct {
+  int32_t rank, swapped;          /* result rank; 1 if the operands were exchanged */
+  const int64_t* bounds;          /* result tiling in TARGET order (layout as tadev_array_desc) */
+  const int32_t* ntiles;
+  const float* norms;             /* result shape in target order; NULL = dense */
+  uint64_t nzero;                 /* zero tiles in the result shape */
+  int64_t nlocal;                 /* local non-zero result tiles */
+  const int64_t* ordinals;        /* [nlocal] ordinal in the target tile grid */
+  const int64_t* elems;           /* [nlocal] elements */
+  const int64_t* offsets;         /* [nlocal] element offset of the tile in the result arena (16-byte aligned) */
+  int64_t arena_elems;            /* doubles the result arena must hold */
+  int32_t Pr, Pc, Mt, Nt, Kt, opA, opB, needs_result_permute;
+} tadev_contraction_info;          /* pointers stay valid until tadev_contraction_destroy */
+
+typedef struct {
+  tadev_summa_stats summa;
+  float permute_ms;               /* up-front argument permutations + result permutation */
+} tadev_contract_stats;
+
+int tadev_contraction_create(tadev_ctx* ctx, const char* target, const char* left_idx, const char* right_idx,
+                             const tadev_array_desc* left, const tadev_array_desc* right, double factor,
+                             const tadev_contract_options* options /* NULL = defaults */, tadev_contraction** out);
+int tadev_contraction_info_get(const tadev_contraction* c, tadev_contraction_info* info);
+int tadev_contraction_owner(const tadev_contraction* c, int64_t target_ordinal, int* owner);
+/* result_arena: device (TADEV_MEM_DEVICE) or pinned host (TADEV_MEM_HOST) memory of arena_elems doubles.
+ * accumulate != 0: C += (the arena holds the previous result with the same layout). */
+int tadev_contraction_eval(tadev_contraction* c, void* result_arena, int result_memory, int accumulate,
+                           tadev_contract_stats* stats);
+int tadev_contraction_destroy(tadev_contraction* c);
+
 /* [host] the schedule the driver will execute, for inspection/tests: per step the root grid
  * column/row and the pair list of this rank. Arrays are caller-allocated with capacities.
  * pairs are (i,j) global tile coordinates in row-major order. */

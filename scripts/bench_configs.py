@@ -129,9 +129,13 @@ if "C3" in which:
     za = (a.shape.norms >= np.float32(SparseShape.threshold())).astype(np.int64)
     zb = (b.shape.norms >= np.float32(SparseShape.threshold())).astype(np.int64)
     pairs = int((za @ zb).sum())
-    run("C3 block-sparse N=65536 tile=512 density=10%", a, b, c, "m,n", "m,k", "k,n", 2.0 * pairs * T ** 3, (5, 6),
-        note=f"{pairs} tile pairs (exact count from the tile lists); apparent 2N^3 = {2.0 * N ** 3:.3e}; "
-             f"result density {1 - c.shape.sparsity() if hasattr(c.shape, 'sparsity') else 1:.3f}")
+    for variant in os.environ.get("C3_VARIANTS", "default").split(","):
+        if variant == "raster0":
+            os.environ["TADEV_RASTER_S"] = "0"
+        else:
+            os.environ.pop("TADEV_RASTER_S", None)
+        run(f"C3 block-sparse N=65536 tile=512 density=10% [{variant}]", a, b, c, "m,n", "m,k", "k,n", 2.0 * pairs * T ** 3, (5, 6),
+            note=f"{pairs} tile pairs (exact count from the tile lists); apparent 2N^3 = {2.0 * N ** 3:.3e}")
     print(json.dumps({"config": "C3", "result_nnz_tiles": len(c.tiles), "result_sparsity": c.shape.sparsity()}), flush=True)
     for x in (a, b, c):
         x.release()

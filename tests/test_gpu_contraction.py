@@ -239,6 +239,27 @@ def test_cont_reference_style_dense_fill(world):
         x.release()
 
 
+def test_cont_accumulate(world):
+    """c("m,n") += a("m,k") * b("k,n") (expressions_impl.h cont_plus_reduce / scale_cont forms): the product
+    is accumulated into the existing result tiles (beta = 1 in the GEMM epilogue), dense and sparse."""
+    rng = np.random.default_rng(5)
+    t = TiledRange1(0, 8, 20, 32)
+    a, A = _dense_array(world, _tr(t, t), rng, True)
+    b, B = _dense_array(world, _tr(t, t), rng, True)
+    c = DistArray(world, _tr(t, t))
+    c["m,n"] = a["m,k"] * b["k,n"]
+    c["m,n"] += 2.0 * (a["m,k"] * b["k,n"])
+    c["m,n"] += a["m,k"] * b["k,n"]
+    assert np.array_equal(c.to_numpy(), 4.0 * (A @ B))
+    (sa, SA, _), (sb, SB, _) = _sparse_pair(world, _tr(t, t), _tr(t, t), 0.5, rng)
+    sc = DistArray(world, _tr(t, t))
+    sc["m,n"] = sa["m,k"] * sb["k,n"]
+    sc["m,n"] += sa["m,k"] * sb["k,n"]
+    assert np.array_equal(sc.to_numpy(), 2.0 * (SA @ SB))
+    for x in (a, b, c, sa, sb, sc):
+        x.release()
+
+
 def test_cont_errors(world):
     t, u = _uniform(8, 4), _uniform(8, 2)
     a = DistArray(world, _tr(t, t)).fill(1.0)

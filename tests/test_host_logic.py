@@ -158,3 +158,34 @@ def test_summa_schedule_matches_oracle(lib, grid, density):
         assert total == Mt * Nt * Kt
     else:
         assert total == int(((~az).astype(int) @ (~bz).astype(int)).sum())
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in tiledarray_b200/_lib.py must have the C layout of include/tadev.h
+    (compiled here with gcc and compared field by field)."""
+    import ctypes as C
+    import subprocess
+    from tiledarray_b200 import _lib as L
+    structs = {"tadev_array_desc": L.ArrayDescC, "tadev_contract_options": L.ContractOptionsC,
+               "tadev_contraction_info": L.ContractionInfoC, "tadev_contract_stats": L.ContractStatsC,
+               "tadev_summa_plan": L.SummaPlanC, "tadev_summa_stats": L.SummaStatsC, "tadev_permute_source": L.PermuteSourceC,
+               "tadev_uniform_source": L.UniformSourceC, "tadev_gemm_group": L.GemmGroup, "tadev_gemm_task": L.GemmTask,
+               "tadev_proc_grid": L.ProcGridC, "tadev_contraction_plan": L.ContractionPlanC}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "tadev.h"', "int main(void){"]
+    for cname, py in structs.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in py._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append("return 0;}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, fname, val = ln.split()
+        got[(cname, fname)] = int(val)
+    for cname, py in structs.items():
+        assert got[(cname, "size")] == C.sizeof(py), cname
+        for fname, _ in py._fields_:
+            assert got[(cname, fname)] == getattr(py, fname).offset, (cname, fname)

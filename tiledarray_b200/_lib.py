@@ -60,6 +60,27 @@ class SummaPlanC(C.Structure):
 SUMMA_A_ON_HOST, SUMMA_B_ON_HOST, SUMMA_C_ON_HOST, SUMMA_A_LAZY, SUMMA_B_LAZY = 1, 2, 4, 8, 16
 
 
+MEM_DEVICE, MEM_HOST, MEM_LAZY = 0, 1, 2
+
+
+class ArrayDescC(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("memory", C.c_int32), ("bounds", C.POINTER(C.c_int64)), ("ntiles", C.POINTER(C.c_int32)),
+                ("norms", C.POINTER(C.c_float)), ("tiles", C.POINTER(C.c_void_p)), ("lazy_seed", C.c_uint64)]
+
+
+class ContractOptionsC(C.Structure):
+    _fields_ = [("exchange_operands", C.c_int32), ("stream_permutes", C.c_int32), ("stream_permute_bytes", C.c_int64),
+                ("depth", C.c_int32), ("steps_per_launch", C.c_int32), ("row_blocks", C.c_int32), ("threshold", C.c_float)]
+
+
+class ContractionInfoC(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("swapped", C.c_int32), ("bounds", C.POINTER(C.c_int64)), ("ntiles", C.POINTER(C.c_int32)),
+                ("norms", C.POINTER(C.c_float)), ("nzero", C.c_uint64), ("nlocal", C.c_int64),
+                ("ordinals", C.POINTER(C.c_int64)), ("elems", C.POINTER(C.c_int64)), ("offsets", C.POINTER(C.c_int64)),
+                ("arena_elems", C.c_int64), ("Pr", C.c_int32), ("Pc", C.c_int32), ("Mt", C.c_int32), ("Nt", C.c_int32),
+                ("Kt", C.c_int32), ("opA", C.c_int32), ("opB", C.c_int32), ("needs_result_permute", C.c_int32)]
+
+
 class UniformSourceC(C.Structure):
     _fields_ = [("ctx", C.c_void_p), ("seed", C.c_uint64)]
 
@@ -73,6 +94,10 @@ class SummaStatsC(C.Structure):
     _fields_ = [("nsteps", C.c_int64), ("nsteps_skipped", C.c_int64), ("npairs", C.c_int64), ("nlaunches", C.c_int64),
                 ("flops", C.c_double), ("bcast_bytes", C.c_int64), ("device_ms", C.c_float), ("row_blocks", C.c_int32),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("lazy_tiles", C.c_int64)]
+
+
+class ContractStatsC(C.Structure):
+    _fields_ = [("summa", SummaStatsC), ("permute_ms", C.c_float)]
 
 
 # every exported symbol of include/tadev.h with its prototype (restype, argtypes)
@@ -116,6 +141,13 @@ PROTOTYPES = {
     "tadev_cyclic_owner": (_i, [_i64, _i64, _i, _i, _P(_i)]),
     "tadev_plan_contraction": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, _P(ContractionPlanC)]),
     "tadev_plan_contraction_opt": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, _P(ContractionPlanC), _P(C.c_int32)]),
+    "tadev_contract_options_default": (_i, [_P(ContractOptionsC)]),
+    "tadev_contraction_create": (_i, [_vp, C.c_char_p, C.c_char_p, C.c_char_p, _P(ArrayDescC), _P(ArrayDescC), _d,
+                                      _P(ContractOptionsC), _P(_vp)]),
+    "tadev_contraction_info_get": (_i, [_vp, _P(ContractionInfoC)]),
+    "tadev_contraction_owner": (_i, [_vp, _i64, _P(_i)]),
+    "tadev_contraction_eval": (_i, [_vp, _vp, _i, _i, _P(ContractStatsC)]),
+    "tadev_contraction_destroy": (_i, [_vp]),
     "tadev_comm_unique_id": (_i, [_vp]),
     "tadev_comm_init": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "tadev_comm_destroy": (_i, [_vp]),

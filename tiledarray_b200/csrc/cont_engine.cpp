@@ -1,0 +1,554 @@
+// cont_engine.cpp — the contraction engine above the SUMMA driver: everything TiledArray's
+// expression layer decides between `c("m,n") = a("m,k") * b("k,n")` and the Summa evaluator.
+//
+// Restates (for device-resident / host-resident / lazy arrays described through the C ABI):
+//   ContEngine::perm_indices + init_indices_ (expressions/cont_engine.h:176-352,
+//       binary_engine.h:101-178, permopt.h:254-376)         -> tadev_plan_contraction(_opt)
+//   ContEngine::init_struct  (cont_engine.h:354-529)         -> op flags, permuted operand structure,
+//       result trange (make_trange :593-637) and result shape (make_shape :642-660 ->
+//       SparseShape::gemm, sparse_shape.h:1589-1691, evaluated by the device screening kernel)
+//   ContEngine::init_distribution (cont_engine.h:537-587)    -> ProcGrid check, cyclic result map
+//   ContEngine::make_dist_eval (cont_engine.h:662-677)       -> tadev_summa_f64
+//   argument-tile permutation (dist_eval/array_eval.h:42,170) -> up-front batched permutes or the
+//       just-in-time permute provider; result-tile permutation (contract_reduce.h:370-378)
+// Host code only: every tile operation is a call into the kernels of this library.
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace {
+
+struct TRange {  // TiledRange: per-dimension tile boundaries
+  std::vector<std::vector<int64_t>> b;
+  int rank() const { return (int)b.size(); }
+  int64_t ntiles(int d) const { return (int64_t)b[d].size() - 1; }
+  int64_t ext(int d, int64_t t) const { return b[d][t + 1] - b[d][t]; }
+  std::vector<int64_t> tiles_shape() const {
+    std::vector<int64_t> s(rank());
+    for (int d = 0; d < rank(); ++d) s[d] = ntiles(d);
+    return s;
+  }
+  int64_t total() const {
+    int64_t n = 1;
+    for (int d = 0; d < rank(); ++d) n *= ntiles(d);
+    return n;
+  }
+};
+
+int64_t ravel(const std::vector<int64_t>& idx, const std::vector<int64_t>& shape) {
+  int64_t o = 0;
+  for (size_t d = 0; d < shape.size(); ++d) o = o * shape[d] + idx[d];
+  return o;
+}
+void unravel(int64_t o, const std::vector<int64_t>& shape, std::vector<int64_t>& idx) {
+  idx.resize(shape.size());
+  for (int d = (int)shape.size() - 1; d >= 0; --d) { idx[d] = o % shape[d]; o /= shape[d]; }
+}
+
+// out[perm(idx)] = in[idx] over a small row-major float tensor (SparseShape::perm, sparse_shape.h:1222)
+std::vector<float> permute_norms(const std::vector<float>& in, const std::vector<int64_t>& shape, const std::vector<int>& perm) {
+  const int R = (int)shape.size();
+  std::vector<int64_t> oshape(R), idx, oidx(R);
+  for (int i = 0; i < R; ++i) oshape[perm[i]] = shape[i];
+  std::vector<float> out(in.size());
+  for (int64_t o = 0; o < (int64_t)in.size(); ++o) {
+    unravel(o, shape, idx);
+    for (int i = 0; i < R; ++i) oidx[perm[i]] = idx[i];
+    out[ravel(oidx, oshape)] = in[o];
+  }
+  return out;
+}
+
+// recursive_outer_product of tile-extent vectors in fp32 (sparse_shape.h:105-132): the association
+// order is part of the bit-exact screening spec.
+std::vector<float> recursive_outer(const TRange& tr, int lo, int hi) {
+  const int dim = hi - lo;
+  if (dim == 1) {
+    std::vector<float> v((size_t)tr.ntiles(lo));
+    for (int64_t t = 0; t < tr.ntiles(lo); ++t) v[t] = (float)tr.ext(lo, t);
+    return v;
+  }
+  const int middle = (dim >> 1) + (dim & 1);
+  const std::vector<float> l = recursive_outer(tr, lo, lo + middle), r = recursive_outer(tr, lo + middle, hi);
+  std::vector<float> out(l.size() * r.size());
+  for (size_t i = 0; i < l.size(); ++i)
+    for (size_t j = 0; j < r.size(); ++j) out[i * r.size() + j] = l[i] * r[j];
+  return out;
+}
+
+// fused (row-major) element extents of the tile grid spanned by dims [lo, hi)
+std::vector<int64_t> fused_ext(const TRange& tr, int lo, int hi) {
+  std::vector<int64_t> e(1, 1);
+  for (int d = lo; d < hi; ++d) {
+    std::vector<int64_t> n;
+    n.reserve(e.size() * tr.ntiles(d));
+    for (int64_t x : e)
+      for (int64_t t = 0; t < tr.ntiles(d); ++t) n.push_back(x * tr.ext(d, t));
+    e.swap(n);
+  }
+  return e;
+}
+
+struct Operand {
+  tadev_array_desc d{};               // as given (pointers into the copies below)
+  TRange tr;                          // original tiling
+  std::vector<int64_t> bounds_flat;
+  std::vector<int32_t> ntiles;
+  std::vector<float> norms;           // empty = dense
+  std::vector<const void*> tiles;     // empty: lazy array whose non-zero tiles are all local
+  std::vector<int> perm;              // explicit permutation (empty = none)
+  TRange ptr;                         // permuted tiling
+  std::vector<float> pnorms;          // permuted norms
+  bool dense() const { return norms.empty(); }
+};
+
+int copy_operand(const tadev_array_desc* a, Operand& o, const char* who) {
+  TADEV_REQUIRE(a && a->rank >= 0 && a->rank <= 16, "%s: bad array descriptor", who);
+  TADEV_REQUIRE(a->rank == 0 || (a->bounds && a->ntiles), "%s: null tiling", who);
+  TADEV_REQUIRE(a->memory >= 0 && a->memory <= 2, "%s: bad memory kind %d", who, a->memory);
+  o.d = *a;
+  size_t off = 0;
+  o.tr.b.resize(a->rank);
+  for (int d = 0; d < a->rank; ++d) {
+    TADEV_REQUIRE(a->ntiles[d] >= 1, "%s: dimension %d has no tiles", who, d);
+    o.tr.b[d].assign(a->bounds + off, a->bounds + off + a->ntiles[d] + 1);
+    for (int t = 0; t < a->ntiles[d]; ++t) TADEV_REQUIRE(o.tr.b[d][t + 1] > o.tr.b[d][t], "%s: tile boundaries must increase", who);
+    off += (size_t)a->ntiles[d] + 1;
+  }
+  const int64_t n = o.tr.total();
+  if (a->norms) o.norms.assign(a->norms, a->norms + n);
+  if (a->tiles) o.tiles.assign(a->tiles, a->tiles + n);
+  TADEV_REQUIRE(a->memory == TADEV_MEM_LAZY || a->tiles, "%s: null tile table", who);
+  return TADEV_OK;
+}
+
+}  // namespace
+
+struct tadev_contraction {
+  tadev_ctx* ctx = nullptr;
+  tadev_contract_options opt{};
+  tadev_contraction_plan plan{};
+  int32_t swapped = 0;
+  double factor = 1.0;
+  Operand L, R;  // after the optional exchange: L is the GEMM's left operand
+  int lo[2], li[2], ro[2], ri[2];
+  std::vector<int64_t> m_ext, n_ext, k_ext;
+  int Mt = 0, Nt = 0, Kt = 0;
+  TRange tr_gemm, tr_target;
+  std::vector<int> perm_res;             // GEMM order -> target order (empty = identity)
+  bool sparse = false;
+  std::vector<float> a_n, b_n, c_n;      // 2-D scaled norms in GEMM orientation [Mt,Kt] [Kt,Nt] [Mt,Nt]
+  std::vector<float> target_norms;       // result shape in target order
+  uint64_t nzero = 0;
+  int Pr = 1, Pc = 1, r = 0, c = 0;
+  // local non-zero result tiles, in GEMM (i,j) row-major order
+  std::vector<int64_t> keys, elems, offs, target_ord;
+  int64_t arena_elems = 0;
+  // flattened target tiling for the info struct
+  std::vector<int64_t> tb_flat;
+  std::vector<int32_t> tn;
+};
+
+static int build_operand_structure(Operand& o, const int32_t* perm_arr, int rank) {
+  o.perm.clear();
+  if (perm_arr[0] >= 0) o.perm.assign(perm_arr, perm_arr + rank);
+  if (o.perm.empty()) { o.ptr = o.tr; o.pnorms = o.norms; return TADEV_OK; }
+  o.ptr.b.resize(rank);
+  for (int i = 0; i < rank; ++i) o.ptr.b[o.perm[i]] = o.tr.b[i];
+  if (!o.dense()) o.pnorms = permute_norms(o.norms, o.tr.tiles_shape(), o.perm);
+  return TADEV_OK;
+}
+
+// SparseShape::gemm on the device: out[Mt,Nt] = |factor| * (a .* ksz) (b .* ksz), hard-zero + count
+static int device_shape_gemm(tadev_ctx* ctx, int Mt, int Nt, int Kt, const std::vector<float>& a, const std::vector<float>& b,
+                             const std::vector<float>& ksz, float abs_factor, float thr, std::vector<float>& out, uint64_t* nzero) {
+  tadev_stream s = (tadev_stream)ctx->streams[0];
+  float *d_a = nullptr, *d_b = nullptr, *d_k = nullptr, *d_o = nullptr;
+  uint64_t* d_z = nullptr;
+  const size_t na = a.size() * 4, nb = b.size() * 4, nk = ksz.size() * 4, no = (size_t)Mt * Nt * 4;
+  int rc = tadev_alloc(ctx, std::max<size_t>(na, 4), (void**)&d_a, s);
+  if (!rc) rc = tadev_alloc(ctx, std::max<size_t>(nb, 4), (void**)&d_b, s);
+  if (!rc) rc = tadev_alloc(ctx, std::max<size_t>(nk, 4), (void**)&d_k, s);
+  if (!rc) rc = tadev_alloc(ctx, std::max<size_t>(no, 4), (void**)&d_o, s);
+  if (!rc) rc = tadev_alloc(ctx, 8, (void**)&d_z, s);
+  if (!rc) rc = tadev_memcpy_h2d(ctx, d_a, a.data(), na, s);
+  if (!rc) rc = tadev_memcpy_h2d(ctx, d_b, b.data(), nb, s);
+  if (!rc && nk) rc = tadev_memcpy_h2d(ctx, d_k, ksz.data(), nk, s);
+  if (!rc) rc = tadev_memset(ctx, d_z, 0, 8, s);
+  if (!rc) rc = tadev_shape_gemm_f32(ctx, s, Mt, Nt, Kt, d_a, d_b, Kt ? d_k : nullptr, abs_factor, thr, d_o, d_z);
+  out.resize((size_t)Mt * Nt);
+  if (!rc) rc = tadev_memcpy_d2h(ctx, out.data(), d_o, no, s);
+  if (!rc) rc = tadev_memcpy_d2h(ctx, nzero, d_z, 8, s);
+  if (!rc) rc = tadev_stream_sync(ctx, s);
+  tadev_free(ctx, d_a, s); tadev_free(ctx, d_b, s); tadev_free(ctx, d_k, s); tadev_free(ctx, d_o, s); tadev_free(ctx, d_z, s);
+  return rc;
+}
+
+extern "C" int tadev_contract_options_default(tadev_contract_options* o) {
+  TADEV_REQUIRE(o, "tadev_contract_options_default: null");
+  memset(o, 0, sizeof(*o));
+  o->exchange_operands = 1;
+  o->stream_permutes = -1;
+  o->stream_permute_bytes = (int64_t)8 << 30;
+  o->threshold = 1.1920928955078125e-07f;  // SparseShape<float> default: FLT_EPSILON (sparse_shape.h:1941)
+  return TADEV_OK;
+}
+
+extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, const char* left_idx, const char* right_idx,
+                                        const tadev_array_desc* left, const tadev_array_desc* right, double factor,
+                                        const tadev_contract_options* options, tadev_contraction** out) {
+  TADEV_REQUIRE(ctx && target && left_idx && right_idx && left && right && out, "tadev_contraction_create: null");
+  std::unique_ptr<tadev_contraction> E(new tadev_contraction());
+  E->ctx = ctx;
+  E->factor = factor;
+  if (options) E->opt = *options; else tadev_contract_options_default(&E->opt);
+  int rc;
+  if (E->opt.exchange_operands) rc = tadev_plan_contraction_opt(target, left_idx, right_idx, &E->plan, &E->swapped);
+  else rc = tadev_plan_contraction(target, left_idx, right_idx, &E->plan);
+  if (rc) return rc;
+  const tadev_contraction_plan& P = E->plan;
+  if ((rc = copy_operand(E->swapped ? right : left, E->L, "tadev_contraction_create(left)"))) return rc;
+  if ((rc = copy_operand(E->swapped ? left : right, E->R, "tadev_contraction_create(right)"))) return rc;
+  TADEV_REQUIRE(E->L.tr.rank() == P.left_rank && E->R.tr.rank() == P.right_rank, "index list rank does not match the array");
+  TADEV_REQUIRE(E->L.d.memory != TADEV_MEM_HOST || P.perm_left[0] < 0, "host-resident left operand needs an explicit permutation: not supported");
+  TADEV_REQUIRE(E->R.d.memory != TADEV_MEM_HOST || P.perm_right[0] < 0, "host-resident right operand needs an explicit permutation: not supported");
+  TADEV_REQUIRE(E->L.d.memory != TADEV_MEM_LAZY || P.perm_left[0] < 0, "a lazy operand that needs an explicit permutation is not supported");
+  TADEV_REQUIRE(E->R.d.memory != TADEV_MEM_LAZY || P.perm_right[0] < 0, "a lazy operand that needs an explicit permutation is not supported");
+  build_operand_structure(E->L, P.perm_left, P.left_rank);
+  build_operand_structure(E->R, P.perm_right, P.right_rank);
+
+  // GemmHelper ranges (math/gemm_helper.h:62-98)
+  const int lr = P.left_rank, rr = P.right_rank, nc = P.inner_rank;
+  if (P.opA == TADEV_OP_N) { E->lo[0] = 0; E->lo[1] = E->li[0] = lr - nc; E->li[1] = lr; }
+  else { E->li[0] = 0; E->li[1] = E->lo[0] = nc; E->lo[1] = lr; }
+  if (P.opB == TADEV_OP_N) { E->ri[0] = 0; E->ri[1] = E->ro[0] = nc; E->ro[1] = rr; }
+  else { E->ro[0] = 0; E->ro[1] = E->ri[0] = rr - nc; E->ri[1] = rr; }
+  const TRange &trA = E->L.ptr, &trB = E->R.ptr;
+  for (int d = 0; d < nc; ++d)
+    TADEV_REQUIRE(trA.b[E->li[0] + d] == trB.b[E->ri[0] + d], "contraction: inner tiled ranges are not congruent");
+  E->m_ext = fused_ext(trA, E->lo[0], E->lo[1]);
+  E->n_ext = fused_ext(trB, E->ro[0], E->ro[1]);
+  E->k_ext = fused_ext(trA, E->li[0], E->li[1]);
+  TADEV_REQUIRE(E->m_ext.size() < (1u << 30) && E->n_ext.size() < (1u << 30) && E->k_ext.size() < (1u << 30), "tile grid too large");
+  E->Mt = (int)E->m_ext.size(); E->Nt = (int)E->n_ext.size(); E->Kt = (int)E->k_ext.size();
+  for (int d = E->lo[0]; d < E->lo[1]; ++d) E->tr_gemm.b.push_back(trA.b[d]);
+  for (int d = E->ro[0]; d < E->ro[1]; ++d) E->tr_gemm.b.push_back(trB.b[d]);
+  if (P.perm_result[0] >= 0) E->perm_res.assign(P.perm_result, P.perm_result + P.result_rank);
+  if (E->perm_res.empty()) E->tr_target = E->tr_gemm;
+  else {
+    E->tr_target.b.resize(P.result_rank);
+    for (int i = 0; i < P.result_rank; ++i) E->tr_target.b[E->perm_res[i]] = E->tr_gemm.b[i];
+  }
+
+  // result shape (make_shape): sparse x sparse -> device screening
+  E->sparse = !(E->L.dense() && E->R.dense());
+  const float thr = E->opt.threshold;
+  if (E->sparse) {
+    TADEV_REQUIRE(!E->L.dense() && !E->R.dense(), "mixed dense/sparse contraction is not supported");
+    const int Mt = E->Mt, Nt = E->Nt, Kt = E->Kt;
+    // 2-D views in GEMM orientation
+    E->a_n.resize((size_t)Mt * Kt);
+    E->b_n.resize((size_t)Kt * Nt);
+    if (P.opA == TADEV_OP_N) E->a_n = E->L.pnorms;
+    else for (int k = 0; k < Kt; ++k) for (int i = 0; i < Mt; ++i) E->a_n[(size_t)i * Kt + k] = E->L.pnorms[(size_t)k * Mt + i];
+    if (P.opB == TADEV_OP_N) E->b_n = E->R.pnorms;
+    else for (int j = 0; j < Nt; ++j) for (int k = 0; k < Kt; ++k) E->b_n[(size_t)k * Nt + j] = E->R.pnorms[(size_t)j * Kt + k];
+    std::vector<float> ksz;
+    if (nc > 0) ksz = recursive_outer(trA, E->li[0], E->li[1]);
+    rc = device_shape_gemm(ctx, Mt, Nt, nc > 0 ? Kt : 0, E->a_n, E->b_n, ksz, (float)std::fabs(factor), thr, E->c_n, &E->nzero);
+    if (rc) return rc;
+    E->target_norms = E->perm_res.empty() ? E->c_n : permute_norms(E->c_n, E->tr_gemm.tiles_shape(), E->perm_res);
+  }
+
+  // distribution (init_distribution): the grid the communicators were built for must be the one
+  // ProcGrid chooses for this result
+  E->Pr = ctx->Pr; E->Pc = ctx->Pc; E->r = ctx->my_r; E->c = ctx->my_c;
+  if (ctx->nranks > 1) {
+    tadev_proc_grid g;
+    const int64_t msum = std::accumulate(E->m_ext.begin(), E->m_ext.end(), (int64_t)0), nsum = std::accumulate(E->n_ext.begin(), E->n_ext.end(), (int64_t)0);
+    if ((rc = tadev_proc_grid_make(ctx->rank, ctx->nranks, E->Mt, E->Nt, msum, nsum, &g))) return rc;
+    TADEV_REQUIRE(g.proc_rows == E->Pr && g.proc_cols == E->Pc, "communicators were built for a %dx%d grid but ProcGrid chooses %dx%d",
+                  E->Pr, E->Pc, g.proc_rows, g.proc_cols);
+  }
+
+  // local non-zero result tiles: C(i,j) -> rank (i % Pr, j % Pc), GEMM row-major order
+  if (E->r >= 0) {
+    const std::vector<int64_t> gshape = E->tr_gemm.tiles_shape(), tshape = E->tr_target.tiles_shape();
+    std::vector<int64_t> gidx, tidx(gshape.size());
+    int64_t off = 0;
+    for (int i = E->r; i < E->Mt; i += E->Pr)
+      for (int j = E->c; j < E->Nt; j += E->Pc) {
+        const int64_t key = (int64_t)i * E->Nt + j;
+        if (E->sparse && E->c_n[key] < thr) continue;
+        const int64_t e = E->m_ext[i] * E->n_ext[j];
+        E->keys.push_back(key); E->elems.push_back(e); E->offs.push_back(off);
+        off += (e + 1) & ~(int64_t)1;
+        if (E->perm_res.empty()) E->target_ord.push_back(key);
+        else {
+          unravel(key, gshape, gidx);
+          for (size_t a = 0; a < gidx.size(); ++a) tidx[E->perm_res[a]] = gidx[a];
+          E->target_ord.push_back(ravel(tidx, tshape));
+        }
+      }
+    E->arena_elems = std::max<int64_t>(off, 2);
+  } else E->arena_elems = 2;
+  for (int d = 0; d < E->tr_target.rank(); ++d) {
+    E->tn.push_back((int32_t)E->tr_target.ntiles(d));
+    E->tb_flat.insert(E->tb_flat.end(), E->tr_target.b[d].begin(), E->tr_target.b[d].end());
+  }
+  *out = E.release();
+  return TADEV_OK;
+}
+
+extern "C" int tadev_contraction_info_get(const tadev_contraction* E, tadev_contraction_info* info) {
+  TADEV_REQUIRE(E && info, "tadev_contraction_info_get: null");
+  memset(info, 0, sizeof(*info));
+  info->rank = E->tr_target.rank();
+  info->swapped = E->swapped;
+  info->bounds = E->tb_flat.data();
+  info->ntiles = E->tn.data();
+  info->norms = E->sparse ? E->target_norms.data() : nullptr;
+  info->nzero = E->nzero;
+  info->nlocal = (int64_t)E->keys.size();
+  info->ordinals = E->target_ord.data();
+  info->elems = E->elems.data();
+  info->offsets = E->offs.data();
+  info->arena_elems = E->arena_elems;
+  info->Pr = E->Pr; info->Pc = E->Pc; info->Mt = E->Mt; info->Nt = E->Nt; info->Kt = E->Kt;
+  info->opA = E->plan.opA; info->opB = E->plan.opB;
+  info->needs_result_permute = E->perm_res.empty() ? 0 : 1;
+  return TADEV_OK;
+}
+
+// owner of a result tile given its ordinal in the TARGET tiling: the cyclic map of the GEMM-order
+// grid (result pmap = grid pmap, cont_engine.h:584)
+extern "C" int tadev_contraction_owner(const tadev_contraction* E, int64_t target_ordinal, int* owner) {
+  TADEV_REQUIRE(E && owner, "tadev_contraction_owner: null");
+  const std::vector<int64_t> tshape = E->tr_target.tiles_shape();
+  TADEV_REQUIRE(target_ordinal >= 0 && target_ordinal < E->tr_target.total(), "tadev_contraction_owner: ordinal out of range");
+  std::vector<int64_t> tidx, gidx(tshape.size());
+  unravel(target_ordinal, tshape, tidx);
+  if (E->perm_res.empty()) gidx = tidx;
+  else for (size_t a = 0; a < tidx.size(); ++a) gidx[a] = tidx[E->perm_res[a]];
+  const int64_t go = ravel(gidx, E->tr_gemm.tiles_shape());
+  *owner = (int)(((go / E->Nt) % E->Pr) * E->Pc + (go % E->Nt) % E->Pc);
+  return TADEV_OK;
+}
+
+extern "C" int tadev_contraction_destroy(tadev_contraction* E) {
+  delete E;
+  return TADEV_OK;
+}
+
+namespace {
+
+// The operand as the SUMMA driver sees it: a table over the fused tile grid holding pointers or
+// provider tokens, plus (for just-in-time permutes) the provider's source tables.
+struct View {
+  std::vector<const double*> table;
+  bool lazy = false;
+  tadev_tile_provider provider = nullptr;
+  tadev_uniform_source usrc{};
+  tadev_permute_source psrc{};
+  std::vector<int64_t> p_ext;      // [ntok][rank]
+  std::vector<const void*> p_src;  // [ntok]
+  double* tmp_arena = nullptr;     // up-front permuted copy
+  void* user() { return provider == tadev_provider_uniform ? (void*)&usrc : (void*)&psrc; }
+};
+
+// position of the tile with PERMUTED ordinal `po` in the fused [rows x cols] table of the GEMM
+inline size_t fused_pos(int64_t po, bool op_n, int64_t rows, int64_t cols) {
+  // op N: the permuted tile grid is already [rows][cols]; op T: it is stored [cols][rows]
+  return op_n ? (size_t)po : (size_t)((po % rows) * cols + po / rows);
+}
+
+int build_view(tadev_contraction* E, Operand& o, bool is_left, View& v, float* permute_ms_acc) {
+  tadev_ctx* ctx = E->ctx;
+  const bool op_n = (is_left ? E->plan.opA : E->plan.opB) == TADEV_OP_N;
+  const int64_t rows = is_left ? E->Mt : E->Kt, cols = is_left ? E->Kt : E->Nt;
+  v.table.assign((size_t)std::max<int64_t>(rows * cols, 1), nullptr);
+  const int64_t n = o.tr.total();
+  const float thr = E->opt.threshold;
+  const int R = o.tr.rank();
+  const std::vector<int64_t> tshape = o.tr.tiles_shape(), pshape = o.ptr.tiles_shape();
+  std::vector<int64_t> idx, pidx(R);
+  auto permuted_ordinal = [&](int64_t ord) -> int64_t {
+    if (o.perm.empty()) return ord;
+    unravel(ord, tshape, idx);
+    for (int i = 0; i < R; ++i) pidx[o.perm[i]] = idx[i];
+    return ravel(pidx, pshape);
+  };
+  if (o.d.memory == TADEV_MEM_LAZY) {
+    v.lazy = true;
+    v.provider = tadev_provider_uniform;
+    v.usrc.ctx = ctx; v.usrc.seed = o.d.lazy_seed;
+    for (int64_t ord = 0; ord < n; ++ord) {
+      if (!o.dense() && o.norms[ord] < thr) continue;
+      if (!o.tiles.empty() && !o.tiles[ord]) continue;  // not local
+      v.table[fused_pos(ord, op_n, rows, cols)] = reinterpret_cast<const double*>((uintptr_t)(ord + 1));
+    }
+    return TADEV_OK;
+  }
+  if (o.perm.empty()) {
+    for (int64_t ord = 0; ord < n; ++ord)
+      if (o.tiles[ord]) v.table[fused_pos(ord, op_n, rows, cols)] = static_cast<const double*>(o.tiles[ord]);
+    return TADEV_OK;
+  }
+  // explicit permutation: gather the local tiles
+  std::vector<int64_t> ords, exts;
+  int64_t bytes = 0;
+  for (int64_t ord = 0; ord < n; ++ord) {
+    if (!o.tiles[ord]) continue;
+    ords.push_back(ord);
+    unravel(ord, tshape, idx);
+    int64_t vol = 1;
+    for (int d = 0; d < R; ++d) { exts.push_back(o.tr.ext(d, idx[d])); vol *= exts.back(); }
+    bytes += vol * 8;
+  }
+  bool stream = E->opt.stream_permutes > 0 || (E->opt.stream_permutes < 0 && bytes > E->opt.stream_permute_bytes);
+  if (stream) {
+    v.lazy = true;
+    v.provider = tadev_provider_permute;
+    v.p_ext = exts;
+    for (int64_t ord : ords) v.p_src.push_back(o.tiles[ord]);
+    v.psrc.ctx = ctx; v.psrc.rank = R;
+    for (int i = 0; i < R; ++i) v.psrc.perm[i] = o.perm[i];
+    v.psrc.extents = v.p_ext.data(); v.psrc.src = v.p_src.data();
+    for (size_t t = 0; t < ords.size(); ++t)
+      v.table[fused_pos(permuted_ordinal(ords[t]), op_n, rows, cols)] = reinterpret_cast<const double*>((uintptr_t)(t + 1));
+    return TADEV_OK;
+  }
+  // up-front: one arena, one batched launch per distinct tile extent
+  tadev_stream s = (tadev_stream)ctx->streams[0];
+  std::vector<int64_t> offs(ords.size());
+  int64_t off = 0;
+  for (size_t t = 0; t < ords.size(); ++t) {
+    int64_t vol = 1;
+    for (int d = 0; d < R; ++d) vol *= exts[t * R + d];
+    offs[t] = off;
+    off += (vol + 1) & ~(int64_t)1;
+  }
+  int rc = tadev_alloc(ctx, (size_t)std::max<int64_t>(off, 2) * 8, (void**)&v.tmp_arena, s);
+  if (rc) return rc;
+  void *e0 = nullptr, *e1 = nullptr;
+  tadev_event_create(ctx, &e0); tadev_event_create(ctx, &e1);
+  tadev_event_record(ctx, e0, s);
+  std::vector<char> done(ords.size(), 0);
+  std::vector<const void*> ins;
+  std::vector<void*> outs;
+  std::vector<int32_t> perm32(o.perm.begin(), o.perm.end());
+  for (size_t t = 0; t < ords.size(); ++t) {
+    if (done[t]) continue;
+    ins.clear(); outs.clear();
+    for (size_t q = t; q < ords.size(); ++q) {
+      if (done[q] || memcmp(&exts[q * R], &exts[t * R], sizeof(int64_t) * R) != 0) continue;
+      ins.push_back(o.tiles[ords[q]]);
+      outs.push_back(v.tmp_arena + offs[q]);
+      done[q] = 1;
+    }
+    rc = tadev_permute_batched(ctx, s, R, &exts[t * R], perm32.data(), 8, (int)ins.size(), ins.data(), outs.data());
+    if (rc) return rc;
+  }
+  tadev_event_record(ctx, e1, s);
+  float ms = 0;
+  tadev_event_elapsed_ms(ctx, e0, e1, &ms);
+  tadev_event_destroy(ctx, e0); tadev_event_destroy(ctx, e1);
+  *permute_ms_acc += ms;
+  for (size_t t = 0; t < ords.size(); ++t)
+    v.table[fused_pos(permuted_ordinal(ords[t]), op_n, rows, cols)] = v.tmp_arena + offs[t];
+  return TADEV_OK;
+}
+
+}  // namespace
+
+extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, int result_memory, int accumulate,
+                                      tadev_contract_stats* stats) {
+  TADEV_REQUIRE(E && result_arena, "tadev_contraction_eval: null");
+  TADEV_REQUIRE(result_memory == TADEV_MEM_DEVICE || result_memory == TADEV_MEM_HOST, "tadev_contraction_eval: the result must be device- or host-resident");
+  TADEV_REQUIRE(result_memory == TADEV_MEM_DEVICE || E->perm_res.empty(), "host-resident result needs a result permutation: not supported");
+  TADEV_REQUIRE(!accumulate || E->perm_res.empty(), "accumulating into a result that needs a permutation is not supported");
+  tadev_ctx* ctx = E->ctx;
+  tadev_stream s = (tadev_stream)ctx->streams[0];
+  if (stats) memset(stats, 0, sizeof(*stats));
+  float permute_ms = 0.0f;
+  View vA, vB;
+  int rc = build_view(E, E->L, true, vA, &permute_ms);
+  if (!rc) rc = build_view(E, E->R, false, vB, &permute_ms);
+  if (rc) return rc;
+
+  // result tiles in GEMM order: straight into the caller's arena, or into a temporary one that is
+  // permuted into the caller's arena afterwards
+  double* gemm_arena = static_cast<double*>(result_arena);
+  if (!E->perm_res.empty()) {
+    rc = tadev_alloc(ctx, (size_t)E->arena_elems * 8, (void**)&gemm_arena, s);
+    if (rc) return rc;
+  }
+  std::vector<double*> c_tab((size_t)std::max<int64_t>((int64_t)E->Mt * E->Nt, 1), nullptr);
+  for (size_t t = 0; t < E->keys.size(); ++t) c_tab[E->keys[t]] = gemm_arena + E->offs[t];
+
+  tadev_summa_plan sp{};
+  sp.Mt = E->Mt; sp.Nt = E->Nt; sp.Kt = E->Kt;
+  sp.m_ext = E->m_ext.data(); sp.n_ext = E->n_ext.data(); sp.k_ext = E->k_ext.data();
+  sp.opA = E->plan.opA; sp.opB = E->plan.opB; sp.alpha = E->factor;
+  sp.a_norms = E->sparse ? E->a_n.data() : nullptr;
+  sp.b_norms = E->sparse ? E->b_n.data() : nullptr;
+  sp.c_norms = E->sparse ? E->c_n.data() : nullptr;
+  sp.threshold = E->opt.threshold;
+  sp.a_tiles = vA.table.data(); sp.b_tiles = vB.table.data(); sp.c_tiles = c_tab.data();
+  sp.accumulate = accumulate ? 1 : 0;
+  sp.depth = E->opt.depth; sp.steps_per_launch = E->opt.steps_per_launch; sp.row_blocks = E->opt.row_blocks;
+  sp.flags = (E->L.d.memory == TADEV_MEM_HOST ? TADEV_SUMMA_A_ON_HOST : 0) | (E->R.d.memory == TADEV_MEM_HOST ? TADEV_SUMMA_B_ON_HOST : 0) |
+             (result_memory == TADEV_MEM_HOST ? TADEV_SUMMA_C_ON_HOST : 0) | (vA.lazy ? TADEV_SUMMA_A_LAZY : 0) | (vB.lazy ? TADEV_SUMMA_B_LAZY : 0);
+  if (vA.lazy) { sp.a_provider = vA.provider; sp.a_user = vA.user(); }
+  if (vB.lazy) { sp.b_provider = vB.provider; sp.b_user = vB.user(); }
+  tadev_summa_stats st{};
+  rc = tadev_summa_f64(ctx, &sp, &st);
+  if (vA.tmp_arena) tadev_free(ctx, vA.tmp_arena, s);
+  if (vB.tmp_arena) tadev_free(ctx, vB.tmp_arena, s);
+  if (rc) { if (gemm_arena != result_arena) tadev_free(ctx, gemm_arena, s); return rc; }
+
+  // result permutation: ContractReduce's post-process (contract_reduce.h:370-378), batched per extent.
+  // The target arena uses the same per-tile offsets (a permuted tile has the same volume).
+  if (!E->perm_res.empty()) {
+    void *e0 = nullptr, *e1 = nullptr;
+    tadev_event_create(ctx, &e0); tadev_event_create(ctx, &e1);
+    tadev_event_record(ctx, e0, s);
+    const int R = E->tr_gemm.rank();
+    const std::vector<int64_t> gshape = E->tr_gemm.tiles_shape();
+    std::vector<int64_t> exts(E->keys.size() * (size_t)R), gidx;
+    for (size_t t = 0; t < E->keys.size(); ++t) {
+      unravel(E->keys[t], gshape, gidx);
+      for (int d = 0; d < R; ++d) exts[t * R + d] = E->tr_gemm.ext(d, gidx[d]);
+    }
+    std::vector<char> done(E->keys.size(), 0);
+    std::vector<const void*> ins;
+    std::vector<void*> outs;
+    std::vector<int32_t> perm32(E->perm_res.begin(), E->perm_res.end());
+    double* target = static_cast<double*>(result_arena);
+    for (size_t t = 0; t < E->keys.size() && !rc; ++t) {
+      if (done[t]) continue;
+      ins.clear(); outs.clear();
+      for (size_t q = t; q < E->keys.size(); ++q) {
+        if (done[q] || memcmp(&exts[q * R], &exts[t * R], sizeof(int64_t) * R) != 0) continue;
+        ins.push_back(gemm_arena + E->offs[q]);
+        outs.push_back(target + E->offs[q]);
+        done[q] = 1;
+      }
+      rc = tadev_permute_batched(ctx, s, R, &exts[t * R], perm32.data(), 8, (int)ins.size(), ins.data(), outs.data());
+    }
+    tadev_event_record(ctx, e1, s);
+    float ms = 0;
+    tadev_event_elapsed_ms(ctx, e0, e1, &ms);
+    tadev_event_destroy(ctx, e0); tadev_event_destroy(ctx, e1);
+    permute_ms += ms;
+    tadev_free(ctx, gemm_arena, s);
+    if (rc) return rc;
+  }
+  if (stats) { stats->summa = st; stats->permute_ms = permute_ms; }
+  return TADEV_OK;
+}

@@ -416,7 +416,7 @@ int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* group
   int rc = tmap_cache_get(ctx, &c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
-  struct Pending { CUtensorMap* dst; int stage_idx; };
+  struct Pending { CUtensorMap* dst; int chunk; };
   std::vector<Pending> pending;
   static const int promo_env = getenv("TADEV_TMAP_L2PROMO") ? atoi(getenv("TADEV_TMAP_L2PROMO")) : 3;
   const CUtensorMapL2promotion l2promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
@@ -452,7 +452,7 @@ int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* group
       tadev_set_error("cuTensorMapEncodeTiled failed (%d) for tile %p [%d x %d]", (int)cr, (const void*)ptr, outer, k);
       return TADEV_ECUDA;
     }
-    pending.push_back({dst, (int)pending.size()});
+    pending.push_back({dst, (int)c->chunks.size() - 1});
     c->index.emplace(key, dst);
     *res = dst;
     return TADEV_OK;
@@ -473,7 +473,8 @@ int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* group
     size_t i = 0;
     while (i < pending.size()) {
       size_t j = i + 1;
-      while (j < pending.size() && pending[j].dst == pending[j - 1].dst + 1) ++j;
+      // (two chunks may be adjacent in the address space: one copy must not span two allocations)
+      while (j < pending.size() && pending[j].chunk == pending[j - 1].chunk && pending[j].dst == pending[j - 1].dst + 1) ++j;
       TADEV_CHECK_CUDA(cudaMemcpyAsync(pending[i].dst, c->h_stage + i, sizeof(CUtensorMap) * (j - i),
                                        cudaMemcpyHostToDevice, c->upload));
       i = j;

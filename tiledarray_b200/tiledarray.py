@@ -431,10 +431,15 @@ class DistArray:
         return self[idx]
 
     def __setitem__(self, idx: str, expr) -> None:
+        if expr is _ASSIGNED:  # c["m,n"] += ... already evaluated by TsrExpr.__iadd__
+            return
         TsrExpr(self, _split(idx)).assign(expr)
 
 
 # ---------------------------------------------------------------------------------------------
+_ASSIGNED = object()
+
+
 class Expr:
     factor = 1.0
 
@@ -453,7 +458,12 @@ class TsrExpr(Expr):
         _ta_assert(len(indices) == array.trange.rank, "index list rank does not match the array")
         self.array, self.indices = array, indices
 
-    def assign(self, expr) -> None:
+    def __iadd__(self, expr):
+        """c("m,n") += a("m,k") * b("k,n"): the product is accumulated into the existing tiles (beta = 1)."""
+        self.assign(expr, accumulate=True)
+        return _ASSIGNED
+
+    def assign(self, expr, accumulate: bool = False) -> None:
         factor = 1.0
         while isinstance(expr, ScalExpr):
             factor *= expr.scalar
@@ -461,7 +471,7 @@ class TsrExpr(Expr):
         _ta_assert(isinstance(expr, MultExpr), "only contraction expressions are implemented (SURVEY §8)")
         _ta_assert(isinstance(expr.left, TsrExpr) and isinstance(expr.right, TsrExpr),
                    "contraction operands must be arrays (nested expressions are out of scope)")
-        ContEngine(self, expr.left, expr.right, factor).eval()
+        ContEngine(self, expr.left, expr.right, factor, accumulate).eval()
 
 
 class ScalExpr(Expr):
@@ -489,226 +499,140 @@ class ContractionStats:
     d2h_bytes: int = 0
     row_blocks: int = 1
     lazy_tiles: int = 0
+    swapped: bool = False
 
 
-class _OperandView:
-    def __init__(self):
-        self.trange = self.shape = None
-        self.ords = np.zeros(0, dtype=np.int64)    # ordinals in the (permuted) tile grid
-        self.vals = np.zeros(0, dtype=np.uint64)   # device/host pointers, or provider tokens
-        self.provider = None                        # address of a tadev_tile_provider (lazy operand)
-        self.user = None                            # its user struct (kept alive here)
-        self.keep: list = []
-        self.tmp: list = []                         # device buffers to free after the contraction
+class _Contraction:
+    """Owner of a native tadev_contraction handle (destroyed with the last reference)."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+
+    def owner(self, ordinal: int) -> int:
+        o = C.c_int()
+        check(self.lib.tadev_contraction_owner(self.handle, ordinal, C.byref(o)))
+        return o.value
+
+    def __del__(self):
+        if self.handle:
+            self.lib.tadev_contraction_destroy(self.handle)
+            self.handle = None
 
 
 class ContEngine:
     """ContEngine (expressions/cont_engine.h:354-677) + Summa hand-off (:662-677).
 
-    init_indices/perm_indices -> tadev_plan_contraction; init_struct -> result trange + shape;
-    init_distribution -> ProcGrid + cyclic maps; make_dist_eval/eval -> tadev_summa_f64.
+    The engine itself is native (csrc/cont_engine.cpp behind tadev_contraction_create/_eval): index
+    analysis and operand exchange, op flags, permuted operand structure, result trange, device shape
+    screening, ProcGrid check, result layout, argument/result tile permutations and the SUMMA call.
+    This class only describes the arrays to it and adopts the result.
     """
 
     last_stats: Optional[ContractionStats] = None
     depth = 0             # SUMMA pipeline depth in windows (0 = default 2; TA_SUMMA_MAX_DEPTH analogue)
     steps_per_launch = 0  # K steps fused into one grouped-GEMM launch (0 = auto)
-    row_blocks = 0        # result row blocks for host-resident results (0 = auto)
+    row_blocks = 0        # result row blocks (0 = auto)
     exchange_operands = True  # evaluate C^T = B^T A^T when that needs fewer explicit tile permutations
     stream_permutes = "auto"  # True/False/"auto": permute argument tiles just in time per SUMMA window
     stream_permute_bytes = 8 << 30  # "auto": stream when the permuted copy would exceed this many bytes
 
-    def __init__(self, result: TsrExpr, left: TsrExpr, right: TsrExpr, factor: float):
-        self.result, self.left, self.right, self.factor = result, left, right, factor
+    def __init__(self, result: TsrExpr, left: TsrExpr, right: TsrExpr, factor: float, accumulate: bool = False):
+        self.result, self.left, self.right, self.factor, self.accumulate = result, left, right, factor, accumulate
         self.world = left.array.world
         self.dev = self.world.dev
-        plan = ContractionPlanC()
-        tgt, li, ri = (",".join(x.indices).encode() for x in (result, left, right))
-        if ContEngine.exchange_operands:
-            swapped = C.c_int32(0)
-            check(self.world.lib.tadev_plan_contraction_opt(tgt, li, ri, C.byref(plan), C.byref(swapped)))
-            if swapped.value:
-                self.left, self.right = right, left
-        else:
-            check(self.world.lib.tadev_plan_contraction(tgt, li, ri, C.byref(plan)))
-        self.plan = plan
 
     @staticmethod
-    def _perm(arr, rank: int) -> Optional[List[int]]:
-        return None if arr[0] < 0 else [int(x) for x in arr[:rank]]
-
-    def _operand_view(self, arr: DistArray, perm: Optional[List[int]]) -> "_OperandView":
-        """The operand as the SUMMA driver sees it: permuted trange/shape plus, per local non-zero tile,
-        its ordinal in the permuted tile grid and either a pointer (device / pinned host) or a provider
-        token. Explicit argument permutations (ArrayEvalImpl/LazyArrayTile + UnaryWrapper<Noop>,
-        dist_eval/array_eval.h:42,170) are either materialised up front into one arena (one batched launch
-        per distinct tile extent) or, for big operands, performed just in time per SUMMA window by the
-        permute provider (no permuted copy in HBM)."""
-        v = _OperandView()
-        dev = self.dev
+    def _describe(arr: DistArray, keep: list) -> "_lib.ArrayDescC":
+        """tadev_array_desc of a DistArray (the arrays it points to are appended to `keep`)."""
+        d = _lib.ArrayDescC()
+        tr = arr.trange
+        bounds = np.asarray([b for dim in tr.dims for b in dim.bounds], dtype=np.int64)
+        ntiles = np.asarray([dim.ntiles for dim in tr.dims], dtype=np.int32)
+        keep += [bounds, ntiles]
+        d.rank = tr.rank
+        d.memory = {"device": _lib.MEM_DEVICE, "host": _lib.MEM_HOST, "lazy": _lib.MEM_LAZY}[arr.memory]
+        d.bounds = bounds.ctypes.data_as(C.POINTER(C.c_int64))
+        d.ntiles = ntiles.ctypes.data_as(C.POINTER(C.c_int32))
+        if not arr.shape.is_dense():
+            norms = np.ascontiguousarray(arr.shape.norms, dtype=f32)
+            keep.append(norms)
+            d.norms = norms.ctypes.data_as(C.POINTER(C.c_float))
+        table = np.zeros(max(tr.ntiles, 1), dtype=np.uint64)
         if arr.memory == "lazy":
-            _ta_assert(perm is None, "a lazy operand that needs an explicit permutation is not supported")
-            ords = np.asarray(arr.local_nonzero_ordinals(), dtype=np.int64)
-            v.trange, v.shape, v.ords, v.vals = arr.trange, arr.shape, ords, (ords + 1).astype(np.uint64)
-            v.user = _lib.UniformSourceC(dev.ctx.value, arr.lazy_seed)
-            v.provider = C.cast(dev.lib.tadev_provider_uniform, C.c_void_p).value
-            return v
-        ords = np.fromiter(arr.tiles.keys(), dtype=np.int64, count=len(arr.tiles))
-        ptrs = np.fromiter((b_.ptr for b_ in arr.tiles.values()), dtype=np.uint64, count=len(arr.tiles))
-        if perm is None:
-            v.trange, v.shape, v.ords, v.vals = arr.trange, arr.shape, ords, ptrs
-            return v
-        rank = len(perm)
-        dims = [None] * rank
-        for i, p in enumerate(perm):
-            dims[p] = arr.trange.dims[i]
-        v.trange = TiledRange(dims)
-        v.shape = arr.shape.perm(perm) if not arr.shape.is_dense() else arr.shape
-        # vectorised index arithmetic: tile index, extent and permuted ordinal of every local tile
-        tshape = arr.trange.tiles_shape
-        idx = np.stack(np.unravel_index(ords, tshape), axis=1) if len(ords) else np.zeros((0, rank), dtype=np.int64)
-        ext = np.stack([np.asarray(d.extents, dtype=np.int64)[idx[:, a]] for a, d in enumerate(arr.trange.dims)], axis=1) \
-            if len(ords) else np.zeros((0, rank), dtype=np.int64)
-        pidx = np.empty_like(idx)
-        pidx[:, perm] = idx
-        v.ords = np.ravel_multi_index(tuple(pidx.T), v.trange.tiles_shape).astype(np.int64) if len(ords) else ords
-        nbytes = int(ext.prod(axis=1).sum()) * 8 if len(ords) else 0
-        stream = ContEngine.stream_permutes
-        if stream == "auto":
-            stream = nbytes > ContEngine.stream_permute_bytes
-        if stream:
-            v.vals = np.arange(1, len(ords) + 1, dtype=np.uint64)
-            v.keep = [np.ascontiguousarray(ext), np.ascontiguousarray(ptrs)]
-            src = _lib.PermuteSourceC()
-            src.ctx, src.rank = dev.ctx.value, rank
-            for i, p in enumerate(perm):
-                src.perm[i] = p
-            src.extents = v.keep[0].ctypes.data_as(C.POINTER(C.c_int64))
-            src.src = v.keep[1].ctypes.data_as(C.POINTER(C.c_void_p))
-            v.user = src
-            v.provider = C.cast(dev.lib.tadev_provider_permute, C.c_void_p).value
-            return v
-        elems = ext.prod(axis=1) if len(ords) else np.zeros(0, dtype=np.int64)
-        padded = (elems + 1) & ~1
-        offs = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
-        arena = dev.alloc(max(int(offs[-1]), 2) * 8)
-        v.vals = (arena.ptr + offs[:-1] * 8).astype(np.uint64)
-        v.tmp = [arena]
-        # one batched launch per distinct tile extent
-        if len(ords):
-            uniq, inv = np.unique(ext, axis=0, return_inverse=True)
-            inv = inv.ravel()
-            for u in range(len(uniq)):
-                sel = np.nonzero(inv == u)[0]
-                dev.permute_batched_ptrs(tuple(int(x) for x in uniq[u]), perm, 8, ptrs[sel], v.vals[sel])
-        return v
+            d.lazy_seed = arr.lazy_seed
+            loc = np.asarray(arr.local_nonzero_ordinals(), dtype=np.int64)
+            table[loc] = 1  # marks the local tiles
+        elif arr.tiles:
+            ords = np.fromiter(arr.tiles.keys(), dtype=np.int64, count=len(arr.tiles))
+            table[ords] = np.fromiter((b_.ptr for b_ in arr.tiles.values()), dtype=np.uint64, count=len(arr.tiles))
+        keep.append(table)
+        d.tiles = table.ctypes.data_as(C.POINTER(C.c_void_p))
+        return d
 
     def eval(self) -> ContractionStats:
-        P, w, dev = self.plan, self.world, self.dev
+        w, dev, lib = self.world, self.dev, self.world.lib
         A, B, Cres = self.left.array, self.right.array, self.result.array
+        _ta_assert(Cres.memory != "lazy", "the result of a contraction cannot be a lazy array")
         A._allocate()
         B._allocate()
         old_host_arena = None
-        if Cres is not A and Cres is not B:
+        old_result = None
+        if self.accumulate:
+            _ta_assert(Cres is not A and Cres is not B, "c += a*b with c among the arguments is not supported")
+            old_result = Cres
+        elif Cres is not A and Cres is not B:
             if Cres.memory == "host" and isinstance(Cres._arena, HostBuffer):
                 old_host_arena, Cres._arena = Cres._arena, None  # page-locking is slow: recycle the pinned arena
             Cres.release()  # hand the old result's memory back to the pool BEFORE allocating the new one
-        nc = P.inner_rank
-        stats = ContractionStats()
-        _ta_assert(A.memory != "host" or P.perm_left[0] < 0, "host-resident left operand needs an explicit permutation: not supported")
-        _ta_assert(B.memory != "host" or P.perm_right[0] < 0, "host-resident right operand needs an explicit permutation: not supported")
-        _ta_assert(Cres.memory == "device" or P.perm_result[0] < 0, "host-resident result needs a result permutation: not supported")
-        _ta_assert(Cres.memory != "lazy", "the result of a contraction cannot be a lazy array")
-        with dev.timer() as tperm:
-            vA = self._operand_view(A, self._perm(P.perm_left, P.left_rank))
-            vB = self._operand_view(B, self._perm(P.perm_right, P.right_rank))
-        trA, shA, trB, shB = vA.trange, vA.shape, vB.trange, vB.shape
-        tmpA, tmpB = vA.tmp, vB.tmp
-        stats.permute_ms = tperm.ms if (tmpA or tmpB) else 0.0
+        keep: list = []
+        dA, dB = self._describe(A, keep), self._describe(B, keep)
+        opt = _lib.ContractOptionsC()
+        check(lib.tadev_contract_options_default(C.byref(opt)))
+        opt.exchange_operands = int(ContEngine.exchange_operands)
+        opt.stream_permutes = -1 if ContEngine.stream_permutes == "auto" else int(bool(ContEngine.stream_permutes))
+        opt.stream_permute_bytes = ContEngine.stream_permute_bytes
+        opt.depth, opt.steps_per_launch, opt.row_blocks = ContEngine.depth, ContEngine.steps_per_launch, ContEngine.row_blocks
+        opt.threshold = SparseShape._threshold
+        handle = C.c_void_p()
+        rc = lib.tadev_contraction_create(dev.ctx, ",".join(self.result.indices).encode(), ",".join(self.left.indices).encode(),
+                                          ",".join(self.right.indices).encode(), C.byref(dA), C.byref(dB), self.factor,
+                                          C.byref(opt), C.byref(handle))
+        if rc == _lib.EINVAL:  # the reference TA_ASSERTs on malformed expressions
+            raise TiledArrayException(lib.tadev_last_error().decode())
+        check(rc)
+        eng = _Contraction(lib, handle)
+        info = _lib.ContractionInfoC()
+        check(lib.tadev_contraction_info_get(handle, C.byref(info)))
 
-        # fused (matrix) views: outer/inner mode ranges of each operand (GemmHelper, gemm_helper.h:62-98)
-        lr, rr = trA.rank, trB.rank
-        lo = (0, lr - nc) if P.opA == _lib.OP_N else (nc, lr)
-        li = (lr - nc, lr) if P.opA == _lib.OP_N else (0, nc)
-        ro = (nc, rr) if P.opB == _lib.OP_N else (0, rr - nc)
-        ri = (0, nc) if P.opB == _lib.OP_N else (rr - nc, rr)
-        for d in range(nc):  # left_right_congruent
-            _ta_assert(trA.dims[li[0] + d] == trB.dims[ri[0] + d], "contraction: inner tiled ranges are not congruent")
-        res_dims = list(trA.dims[lo[0]:lo[1]]) + list(trB.dims[ro[0]:ro[1]])
-        tr_gemm = TiledRange(res_dims)  # result in GEMM order (make_trange, cont_engine.h:593-637)
-
-        def fused_ext(dims):
-            ext = np.ones(1, dtype=np.int64)
-            for d in dims:
-                ext = np.multiply.outer(ext, np.asarray(d.extents, dtype=np.int64)).ravel()
-            return ext
-
-        m_ext, n_ext, k_ext = fused_ext(trA.dims[lo[0]:lo[1]]), fused_ext(trB.dims[ro[0]:ro[1]]), fused_ext(trA.dims[li[0]:li[1]])
-        Mt, Nt, Kt = len(m_ext), len(n_ext), len(k_ext)
-
-        # result shape (make_shape, cont_engine.h:642-660)
-        perm_res = self._perm(P.perm_result, P.result_rank)
-        sparse = not (shA.is_dense() and shB.is_dense())
-        if sparse:
-            _ta_assert(not shA.is_dense() and not shB.is_dense(), "mixed dense/sparse contraction is not supported")
-            sh_gemm = shA.gemm(shB, self.factor, P.opA, P.opB, nc)
-        else:
-            sh_gemm = DenseShape()
-
-        # target structure
-        if perm_res is None:
-            tr_target = tr_gemm
-        else:
-            dims = [None] * len(perm_res)
-            for i, p in enumerate(perm_res):
-                dims[p] = tr_gemm.dims[i]
-            tr_target = TiledRange(dims)
+        # result structure
+        dims, off = [], 0
+        for d in range(info.rank):
+            n = info.ntiles[d]
+            dims.append(TiledRange1(*[info.bounds[off + t] for t in range(n + 1)]))
+            off += n + 1
+        tr_target = TiledRange(dims)
         _ta_assert(Cres.trange == tr_target or not Cres.tiles and Cres.trange.rank == tr_target.rank,
                    "result array tiling does not match the expression")
-
-        # distribution (init_distribution, cont_engine.h:537-587)
-        Pr, Pc = w.grid or (1, 1)
-        r, c = w.grid_pos
-        if w.size > 1:
-            g = w.proc_grid(Mt, Nt, int(m_ext.sum()), int(n_ext.sum()))
-            _ta_assert((g.proc_rows, g.proc_cols) == (Pr, Pc),
-                       f"communicators were built for a {Pr}x{Pc} grid but ProcGrid chooses {g.proc_rows}x{g.proc_cols}")
-
-        def norms_2d(sh, rows, cols, transposed):
-            if sh.is_dense():
-                return None
-            n2 = sh.norms.reshape((cols, rows) if transposed else (rows, cols))
-            return np.ascontiguousarray(n2.T if transposed else n2, dtype=f32)
-
-        a_n = norms_2d(shA, Mt, Kt, P.opA == _lib.OP_T)
-        b_n = norms_2d(shB, Kt, Nt, P.opB == _lib.OP_T)
-        c_n = None if sh_gemm.is_dense() else np.ascontiguousarray(sh_gemm.norms.reshape(Mt, Nt), dtype=f32)
-        thr = SparseShape._threshold
-
-        # tile tables in fused (row-major) ordinals
-        a_tab = np.zeros(max(Mt * Kt, 1), dtype=np.uint64)
-        b_tab = np.zeros(max(Kt * Nt, 1), dtype=np.uint64)
-        c_tab = np.zeros(max(Mt * Nt, 1), dtype=np.uint64)
-        if len(vA.ords):
-            oa = vA.ords
-            a_tab[oa if P.opA == _lib.OP_N else (oa % Mt) * Kt + oa // Mt] = vA.vals
-        if len(vB.ords):
-            ob = vB.ords
-            b_tab[ob if P.opB == _lib.OP_N else (ob % Kt) * Nt + ob // Kt] = vB.vals
-        # result tiles in GEMM order, owned cyclically by (i % Pr, j % Pc)
-        # (vectorised: block-sparse results have 10^4 tiles and this is on the timed path)
-        if r >= 0:
-            I, J = np.arange(r, Mt, Pr), np.arange(c, Nt, Pc)
-            keep = np.ones((len(I), len(J)), dtype=bool) if c_n is None else (c_n[np.ix_(I, J)] >= f32(thr))
-            ii, jj = np.nonzero(keep)
-            ci, cj = I[ii], J[jj]
+        nloc = info.nlocal
+        ords = np.ctypeslib.as_array(info.ordinals, shape=(nloc,)).copy() if nloc else np.zeros(0, dtype=np.int64)
+        elems = np.ctypeslib.as_array(info.elems, shape=(nloc,)).copy() if nloc else np.zeros(0, dtype=np.int64)
+        offs = np.ctypeslib.as_array(info.offsets, shape=(nloc,)).copy() if nloc else np.zeros(0, dtype=np.int64)
+        if info.norms:
+            norms = np.ctypeslib.as_array(info.norms, shape=(max(tr_target.ntiles, 1),)).copy().reshape(tr_target.tiles_shape)
+            sv = [np.asarray(d.extents, dtype=f32) for d in tr_target.dims]
+            new_shape = SparseShape(w, None, None, _prebuilt=(norms, sv, int(info.nzero), SparseShape._threshold))
         else:
-            ci = cj = np.zeros(0, dtype=np.int64)
-        elems = (m_ext[ci] * n_ext[cj]).astype(np.int64)
-        padded = (elems + 1) & ~1
-        offs = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
+            new_shape = DenseShape()
+
+        # result arena
         c_on_host = Cres.memory == "host"
-        need_bytes = max(int(offs[-1]), 2) * 8
-        if c_on_host:
+        need_bytes = int(info.arena_elems) * 8
+        if self.accumulate:
+            _ta_assert(old_result.trange == tr_target and old_result._arena is not None and old_result._arena.nbytes >= need_bytes
+                       and sorted(old_result.tiles) == sorted(ords.tolist()),
+                       "c += a*b: the existing result must have the tiling and tile set of the product")
+            arena = old_result._arena
+        elif c_on_host:
             if old_host_arena is not None and old_host_arena.nbytes >= need_bytes:
                 arena = old_host_arena
             else:
@@ -717,104 +641,35 @@ class ContEngine:
                 arena = HostBuffer(need_bytes)
         else:
             arena = dev.alloc(need_bytes)
-        keys = (ci * Nt + cj).astype(np.int64)
-        c_tab[keys] = (arena.ptr + offs[:-1] * 8).astype(np.uint64)
-        local_c = list(zip(ci.tolist(), cj.tolist()))
-        sizes = padded.tolist()
-        if c_on_host:
-            gemm_tiles = {k_: HostBuffer(e_ * 8, arena.ptr + o_ * 8, owned=False)
-                          for k_, o_, e_ in zip(keys.tolist(), offs[:-1].tolist(), elems.tolist())}
-        else:
-            gemm_tiles = {k_: DeviceBuffer(dev, arena.ptr + o_ * 8, e_ * 8, False)
-                          for k_, o_, e_ in zip(keys.tolist(), offs[:-1].tolist(), elems.tolist())}
+        st = _lib.ContractStatsC()
+        check(lib.tadev_contraction_eval(handle, arena.ptr, _lib.MEM_HOST if c_on_host else _lib.MEM_DEVICE,
+                                         int(self.accumulate), C.byref(st)))
+        stats = ContractionStats()
+        sm = st.summa
+        stats.nsteps, stats.nsteps_skipped, stats.npairs = sm.nsteps, sm.nsteps_skipped, sm.npairs
+        stats.nlaunches, stats.flops, stats.bcast_bytes, stats.device_ms = sm.nlaunches, sm.flops, sm.bcast_bytes, sm.device_ms
+        stats.h2d_bytes, stats.d2h_bytes, stats.row_blocks, stats.lazy_tiles = sm.h2d_bytes, sm.d2h_bytes, sm.row_blocks, sm.lazy_tiles
+        stats.permute_ms = st.permute_ms
+        stats.swapped = bool(info.swapped)
 
-        sp = SummaPlanC()
-        sp.Mt, sp.Nt, sp.Kt = Mt, Nt, Kt
-        sp.m_ext = m_ext.ctypes.data_as(C.POINTER(C.c_int64))
-        sp.n_ext = n_ext.ctypes.data_as(C.POINTER(C.c_int64))
-        sp.k_ext = k_ext.ctypes.data_as(C.POINTER(C.c_int64))
-        sp.opA, sp.opB, sp.alpha = P.opA, P.opB, self.factor
-        fp = C.POINTER(C.c_float)
-        sp.a_norms = a_n.ctypes.data_as(fp) if a_n is not None else None
-        sp.b_norms = b_n.ctypes.data_as(fp) if b_n is not None else None
-        sp.c_norms = c_n.ctypes.data_as(fp) if c_n is not None else None
-        sp.threshold = thr
-        vpp = C.POINTER(C.c_void_p)
-        sp.a_tiles, sp.b_tiles, sp.c_tiles = (a_tab.ctypes.data_as(vpp), b_tab.ctypes.data_as(vpp),
-                                              c_tab.ctypes.data_as(vpp))
-        sp.accumulate, sp.depth, sp.steps_per_launch = 0, ContEngine.depth, ContEngine.steps_per_launch
-        sp.flags = ((_lib.SUMMA_A_ON_HOST if A.memory == "host" else 0) | (_lib.SUMMA_B_ON_HOST if B.memory == "host" else 0) |
-                    (_lib.SUMMA_C_ON_HOST if c_on_host else 0) | (_lib.SUMMA_A_LAZY if vA.provider else 0) |
-                    (_lib.SUMMA_B_LAZY if vB.provider else 0))
-        if vA.provider:
-            sp.a_provider, sp.a_user = vA.provider, C.cast(C.pointer(vA.user), C.c_void_p)
-        if vB.provider:
-            sp.b_provider, sp.b_user = vB.provider, C.cast(C.pointer(vB.user), C.c_void_p)
-        sp.row_blocks = ContEngine.row_blocks
-        st = SummaStatsC()
-        check(w.lib.tadev_summa_f64(dev.ctx, C.byref(sp), C.byref(st)))
-        stats.nsteps, stats.nsteps_skipped, stats.npairs = st.nsteps, st.nsteps_skipped, st.npairs
-        stats.nlaunches, stats.flops, stats.bcast_bytes, stats.device_ms = st.nlaunches, st.flops, st.bcast_bytes, st.device_ms
-        stats.h2d_bytes, stats.d2h_bytes, stats.row_blocks = st.h2d_bytes, st.d2h_bytes, st.row_blocks
-        stats.lazy_tiles = st.lazy_tiles
-        for b in tmpA + tmpB:
-            b.free()
-
-        # hand the result tiles to the target array (finalize, contraction_eval.h:1180-1269; the
-        # result permutation is ContractReduce's post-process, contract_reduce.h:370-378)
-        Cres.release()
-        Cres.trange = tr_target
-        if sh_gemm.is_dense():
-            Cres.shape = DenseShape()
-        else:
-            Cres.shape = sh_gemm.perm(perm_res) if perm_res is not None else sh_gemm
-        owner_map: Dict[int, int] = {}
-        if perm_res is None:
-            Cres._arena = arena
-            Cres.tiles = gemm_tiles
-        else:
-            with dev.timer() as tp2:
-                out_arena = dev.alloc(arena.nbytes)
-                off = 0
-                by_extent: Dict[Tuple[int, ...], Tuple[list, list]] = {}
-                for (i, j), s in zip(local_c, sizes):
-                    o = i * Nt + j
-                    idx = tr_gemm.tile_index(o)
-                    ext = tr_gemm.tile_extent(idx)
-                    pidx = [0] * len(perm_res)
-                    for a_, p in enumerate(perm_res):
-                        pidx[p] = idx[a_]
-                    dst = out_arena.view(off * 8, gemm_tiles[o].nbytes)
-                    srcs, dsts = by_extent.setdefault(tuple(ext), ([], []))
-                    srcs.append(gemm_tiles[o])
-                    dsts.append(dst)
-                    Cres.tiles[tr_target.tile_ordinal(pidx)] = dst
-                    off += s
-                for ext, (srcs, dsts) in by_extent.items():
-                    dev.permute_batched(ext, perm_res, 8, srcs, dsts)
-            stats.permute_ms += tp2.ms
-            arena.free()
-            Cres._arena = out_arena
-        # ownership of the target ordinals follows the GEMM-order cyclic map
-        gemm_shape = tr_gemm.tiles_shape
-
-        def owner(ordinal: int, _perm=perm_res, _tr=tr_target, _Pr=Pr, _Pc=Pc, _Nt=Nt, _gs=gemm_shape) -> int:
-            idx = _tr.tile_index(ordinal)
-            if _perm is not None:
-                gidx = [idx[p] for p in _perm]
+        # adopt the result (finalize, contraction_eval.h:1180-1269)
+        if not self.accumulate:
+            Cres.release()
+            Cres.trange, Cres.shape, Cres._arena = tr_target, new_shape, arena
+            if c_on_host:
+                Cres.tiles = {o_: HostBuffer(e_ * 8, arena.ptr + f_ * 8, owned=False)
+                              for o_, f_, e_ in zip(ords.tolist(), offs.tolist(), elems.tolist())}
             else:
-                gidx = list(idx)
-            go = int(np.ravel_multi_index(tuple(gidx), _gs)) if _gs else 0
-            return ((go // _Nt) % _Pr) * _Pc + (go % _Nt) % _Pc
-
-        Cres._owner = owner
+                Cres.tiles = {o_: DeviceBuffer(dev, arena.ptr + f_ * 8, e_ * 8, False)
+                              for o_, f_, e_ in zip(ords.tolist(), offs.tolist(), elems.tolist())}
+            Cres._owner = eng.owner
         ContEngine.last_stats = stats
         return stats
 
 
 # ---------------------------------------------------------------------------------------------
 def summa_arrays(world: World, trA: TiledRange, trB: TiledRange, shapeA=None, shapeB=None,
-                 memory: str = "device") -> Tuple[DistArray, DistArray]:
+                 memory: str = "device", lazy_seeds=(None, None)) -> Tuple[DistArray, DistArray]:
     """Create the operands of ``C[m,n] = A[m,k] * B[k,n]`` (matrices) distributed with the
     process grid's cyclic maps (make_row_phase_pmap / make_col_phase_pmap, proc_grid.h:566-597)
     and with arenas ordered so that SUMMA panels are contiguous."""
@@ -826,4 +681,7 @@ def summa_arrays(world: World, trA: TiledRange, trB: TiledRange, shapeA=None, sh
     ownB = lambda o: ((o // Nt) % Pr) * Pc + (o % Nt) % Pc  # noqa: E731
     orderA = [i * Kt + k for k in range(Kt) for i in range(Mt)]  # column panels contiguous
     orderB = [k * Nt + j for k in range(Kt) for j in range(Nt)]  # row panels contiguous
-    return (DistArray(world, trA, shapeA, ownA, orderA, memory), DistArray(world, trB, shapeB, ownB, orderB, memory))
+    memA = "lazy" if lazy_seeds[0] is not None else memory
+    memB = "lazy" if lazy_seeds[1] is not None else memory
+    return (DistArray(world, trA, shapeA, ownA, orderA, memA, lazy_seeds[0]),
+            DistArray(world, trB, shapeB, ownB, orderB, memB, lazy_seeds[1]))
