@@ -81,6 +81,92 @@ __global__ void __launch_bounds__(256) transpose_tiled_kernel(const T* __restric
   }
 }
 
+// Fast path of the tiled transpose for 8-byte elements and full-size 64 x 32 tiles (the shape the
+// planner picks whenever both modes are long): ncu on the generic kernel showed 71 warp
+// instructions per 32 elements (64-bit index math and predicates per element, 64-bit divisions per
+// block) and the issue slots, not DRAM, as the limiter (issue 60 %, dram 60 %). Here every thread
+// keeps a fixed (column, first row) and walks rows by a constant stride: one add per access,
+// block decode in 32-bit, all loads of a thread in flight before the first shared-memory store.
+// VEC: 16-byte global loads/stores (two elements along a on the way in, two along b on the way out).
+template <int TA, int TB, bool VEC>
+__global__ void __launch_bounds__(256) transpose_fast_kernel(const uint64_t* __restrict__ in0, uint64_t* __restrict__ out0,
+                                                             const void* const* __restrict__ ins,
+                                                             void* const* __restrict__ outs, PermParams p) {
+  constexpr int LDT = TA + 1;
+  __shared__ uint64_t tile[TB * LDT];
+  const uint64_t* __restrict__ in = ins ? static_cast<const uint64_t*>(ins[blockIdx.y]) : in0;
+  uint64_t* __restrict__ out = outs ? static_cast<uint64_t*>(outs[blockIdx.y]) : out0;
+  uint32_t bid = blockIdx.x;
+  const uint32_t nTa = (uint32_t)p.nTa, nTb = (uint32_t)p.nTb;
+  const uint32_t ta = bid % nTa; bid /= nTa;
+  const uint32_t tb = bid % nTb; bid /= nTb;
+  int64_t base_in = 0, base_out = 0;
+  for (int d = 0; d < p.nother; ++d) {
+    const int m = p.other[d];
+    const uint32_t e = (uint32_t)p.ext[m];
+    const uint32_t i = bid % e;
+    bid /= e;
+    base_in += (int64_t)i * p.sin[m];
+    base_out += (int64_t)i * p.sout[m];
+  }
+  const int64_t a0 = (int64_t)ta * TA, b0 = (int64_t)tb * TB;
+  const int ra = (int)min((int64_t)TA, p.ext[p.a] - a0), rb = (int)min((int64_t)TB, p.ext[p.b] - b0);
+  const bool full = (ra == TA) && (rb == TB);
+  const int64_t sin_b = p.sin[p.b], sout_a = p.sout[p.a];
+  const uint64_t* __restrict__ src = in + base_in + b0 * sin_b + a0;
+  uint64_t* __restrict__ dst = out + base_out + a0 * sout_a + b0;
+  const int tid = threadIdx.x;
+  if (VEC) {
+    // in: TA/2 threads per row, 256/(TA/2) rows per pass
+    constexpr int TPR = TA / 2, RPP = 256 / TPR, NP = TB / RPP;
+    const int ia = (tid % TPR) * 2, ib0 = tid / TPR;
+    ulonglong2 v[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int ib = ib0 + i * RPP;
+      if (full || (ia < ra && ib < rb)) v[i] = *reinterpret_cast<const ulonglong2*>(src + (int64_t)ib * sin_b + ia);  // ra is even
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int ib = ib0 + i * RPP;
+      tile[ib * LDT + ia] = v[i].x;
+      tile[ib * LDT + ia + 1] = v[i].y;
+    }
+    __syncthreads();
+    // out: TB/2 threads per output row, 256/(TB/2) rows per pass
+    constexpr int TPO = TB / 2, OPP = 256 / TPO, NO = TA / OPP;
+    const int ob = (tid % TPO) * 2, oa0 = tid / TPO;
+#pragma unroll
+    for (int i = 0; i < NO; ++i) {
+      const int oa = oa0 + i * OPP;
+      ulonglong2 w;
+      w.x = tile[ob * LDT + oa];
+      w.y = tile[(ob + 1) * LDT + oa];
+      if (full || (oa < ra && ob < rb)) *reinterpret_cast<ulonglong2*>(dst + (int64_t)oa * sout_a + ob) = w;  // rb is even
+    }
+  } else {
+    constexpr int RPP = 256 / TA, NP = TB / RPP;
+    const int ia = tid % TA, ib0 = tid / TA;
+    uint64_t v[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int ib = ib0 + i * RPP;
+      if (full || (ia < ra && ib < rb)) v[i] = src[(int64_t)ib * sin_b + ia];
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) tile[(ib0 + i * RPP) * LDT + ia] = v[i];
+    __syncthreads();
+    constexpr int OPP = 256 / TB, NO = TA / OPP;
+    const int ob = tid % TB, oa0 = tid / TB;
+#pragma unroll
+    for (int i = 0; i < NO; ++i) {
+      const int oa = oa0 + i * OPP;
+      const uint64_t w = tile[ob * LDT + oa];
+      if (full || (oa < ra && ob < rb)) dst[(int64_t)oa * sout_a + ob] = w;
+    }
+  }
+}
+
 // Rows (the preserved, contiguous last mode) are copied whole; V is the vector type, I the index
 // type (32-bit whenever the tile has < 2^31 vector elements: 64-bit div/mod costs ~10x more).
 // Each thread moves 4 independent chunks per iteration (loads first, then stores).
@@ -234,10 +320,27 @@ int plan_permute(int rank, const int64_t* extent, const int32_t* perm, int elem_
 
 template <typename T>
 int launch_tiled(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const void* in, void* out,
-                 const void* const* d_ins, void* const* d_outs, int ntiles) {
+                 const void* const* d_ins, void* const* d_outs, int ntiles, bool ptrs_al16) {
   int64_t blocks = p.nTa * p.nTb;
   for (int d = 0; d < p.nother; ++d) blocks *= p.ext[p.other[d]];
   TADEV_REQUIRE(blocks < (1ll << 31), "tadev_permute: tile too large for one launch");
+  static const int fast_env = getenv("TADEV_PERM_FAST") ? atoi(getenv("TADEV_PERM_FAST")) : 2;  // 0 generic, 1 scalar, 2 vector
+  bool ext32 = true;
+  for (int d = 0; d < p.R; ++d) ext32 = ext32 && p.ext[d] < (1ll << 31);
+  if (sizeof(T) == 8 && p.TA == 64 && p.TB == 32 && fast_env > 0 && ext32) {
+    // 16-byte accesses need every row start 16-byte aligned on both sides: even extents along a and
+    // b make all strides even (the other modes' strides are multiples of those extents)
+    bool vec = fast_env > 1 && ptrs_al16 && (p.ext[p.a] % 2 == 0) && (p.ext[p.b] % 2 == 0);
+    for (int d = 0; d < p.R && vec; ++d) {
+      if (d != p.a && (p.sin[d] & 1)) vec = false;
+      if (d != p.b && (p.sout[d] & 1)) vec = false;
+    }
+    if (vec) transpose_fast_kernel<64, 32, true><<<dim3((unsigned)blocks, (unsigned)ntiles), 256, 0, s>>>((const uint64_t*)in, (uint64_t*)out, d_ins, d_outs, p);
+    else transpose_fast_kernel<64, 32, false><<<dim3((unsigned)blocks, (unsigned)ntiles), 256, 0, s>>>((const uint64_t*)in, (uint64_t*)out, d_ins, d_outs, p);
+    ctx->launches++;
+    TADEV_CHECK_CUDA(cudaGetLastError());
+    return TADEV_OK;
+  }
   const size_t smem = sizeof(T) * (size_t)(p.TA + 1) * p.TB;
   auto kern = transpose_tiled_kernel<T>;
   if (smem > 48 * 1024) TADEV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -279,9 +382,9 @@ int launch_plan(tadev_ctx* ctx, cudaStream_t s, Plan& plan, bool ptrs_al16, cons
     if (eb == 8) return launch_rowcopy<uint64_t>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
     return launch_rowcopy<uint4>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
   }
-  if (eb == 4) return launch_tiled<uint32_t>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
-  if (eb == 8) return launch_tiled<uint64_t>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
-  return launch_tiled<uint4>(ctx, s, p, in, out, d_ins, d_outs, ntiles);
+  if (eb == 4) return launch_tiled<uint32_t>(ctx, s, p, in, out, d_ins, d_outs, ntiles, ptrs_al16);
+  if (eb == 8) return launch_tiled<uint64_t>(ctx, s, p, in, out, d_ins, d_outs, ntiles, ptrs_al16);
+  return launch_tiled<uint4>(ctx, s, p, in, out, d_ins, d_outs, ntiles, ptrs_al16);
 }
 
 }  // namespace

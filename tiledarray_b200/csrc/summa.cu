@@ -253,6 +253,33 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     b_cache_off[si] = b_cache_elems;
     if (b_cache && (S.steps[si].bcast_b || b_stg)) b_cache_elems += e;
   }
+  // ---- global windows. NCCL may reorder the operations inside one group, so two ranks of a
+  // communicator must put the same broadcasts into the same group: window boundaries are therefore
+  // derived from replicated data only (globally active steps, a byte bound that is the maximum
+  // over all grid positions), never from this rank's own compute pattern.
+  std::vector<int> win_of_k(std::max(Kt, 1), 0);
+  {
+    auto a_nz = [&](int i, int k) { return !P.a_norms || P.a_norms[(size_t)i * Kt + k] >= P.threshold; };
+    auto b_nz = [&](int k, int j) { return !P.b_norms || P.b_norms[(size_t)k * Nt + j] >= P.threshold; };
+    int nwin = 0, cnt = 0;
+    size_t gbytes = 0;
+    std::vector<size_t> per_r(Pr), per_c(Pc);
+    for (int k = 0; k < Kt; ++k) {
+      std::fill(per_r.begin(), per_r.end(), 0);
+      std::fill(per_c.begin(), per_c.end(), 0);
+      bool any_a = false, any_b = false;
+      for (int i = 0; i < Mt; ++i) if (a_nz(i, k)) { any_a = true; per_r[i % Pr] += pad2((size_t)P.m_ext[i] * P.k_ext[k]) * 8; }
+      for (int j = 0; j < Nt; ++j) if (b_nz(k, j)) { any_b = true; per_c[j % Pc] += pad2((size_t)P.k_ext[k] * P.n_ext[j]) * 8; }
+      win_of_k[k] = nwin;
+      if (!(any_a && any_b)) continue;  // no rank computes or broadcasts in this step
+      size_t need = 0;
+      if (a_stg || Pc > 1) need += *std::max_element(per_r.begin(), per_r.end());
+      if ((b_stg || Pr > 1) && !b_cache) need += *std::max_element(per_c.begin(), per_c.end());
+      const int wcap = (nwin == 0) ? 1 : W;  // the very first window is a single step: the pipeline fills quickly
+      if (cnt > 0 && (cnt >= wcap || gbytes + need > kMaxWindowBytes)) { ++nwin; cnt = 0; gbytes = 0; win_of_k[k] = nwin; }
+      ++cnt; gbytes += need;
+    }
+  }
   for (int b = 0; b < nb; ++b) {
     const int L = (int)my_rows.size();
     const int lo = (int)((int64_t)L * b / nb), hi = (int)((int64_t)L * (b + 1) / nb);
@@ -274,21 +301,20 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
       bs.compute = !bs.a_rows.empty() && !st.b_cols.empty();
       if (bs.compute || bs.bcast_a || bs.bcast_b) bsteps[b].push_back(std::move(bs));
     }
+    // windows are GLOBAL k-ranges (win_of_k): every rank of a row/column communicator then issues
+    // identically composed NCCL groups (same broadcasts in the same group) whatever its own sparsity
     Window cur;
-    int ncomp = 0;
+    int cur_win = -1;
     for (int x = 0; x < (int)bsteps[b].size(); ++x) {
       const BlockStep& bs = bsteps[b][x];
       size_t need = 0;
       if (bs.bcast_a || (a_stg && bs.compute)) need += bs.a_elems * 8;
       const bool b_to_cache = b_cache && (bs.st->bcast_b || b_stg);
       if (!b_to_cache && (bs.bcast_b || (b_stg && bs.compute))) need += bs.b_elems * 8;
-      // the very first window is a single step so that the pipeline fills quickly
-      const int wcap = (b == 0 && bwins[b].empty()) ? 1 : W;
-      if (!cur.steps.empty() && (ncomp >= wcap || cur.bytes + need > kMaxWindowBytes)) {
-        bwins[b].push_back(std::move(cur)); cur = Window(); ncomp = 0;
-      }
+      const int gw = win_of_k[bs.st->k];
+      if (!cur.steps.empty() && gw != cur_win) { bwins[b].push_back(std::move(cur)); cur = Window(); }
+      cur_win = gw;
       cur.steps.push_back(x); cur.bytes += need;
-      if (bs.compute) ++ncomp;
     }
     if (!cur.steps.empty()) bwins[b].push_back(std::move(cur));
     for (auto& w : bwins[b]) max_bytes = std::max(max_bytes, w.bytes);
@@ -552,6 +578,12 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
         mark("h2d_done", b, wi, sh);
         TADEV_CHECK_CUDA(cudaEventRecord(h2d_done[d], sh));
         TADEV_CHECK_CUDA(cudaStreamWaitEvent(any_bcast ? sc : s0, h2d_done[d], 0));
+      }
+      if (trace) {
+        fprintf(stderr, "[tadev summa rank %d] block %d window %d slot %d: %zu steps, h2d %d, ring_touched %d\n", ctx->rank, b, wi, d,
+                win.steps.size(), (int)any_h2d, (int)ring_touched);
+        for (auto& bc : row_bcasts) fprintf(stderr, "[tadev summa rank %d]   row bcast root %d bytes %zu\n", ctx->rank, bc.root, bc.bytes);
+        for (auto& bc : col_bcasts) fprintf(stderr, "[tadev summa rank %d]   col bcast root %d bytes %zu\n", ctx->rank, bc.root, bc.bytes);
       }
       if (any_bcast) {
         // same (communicator, k) order on every rank of a group => no cross-communicator deadlock
