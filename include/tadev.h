@@ -375,6 +375,16 @@ int tadev_summa_steps(int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt, cons
                       int32_t* step_flags, int32_t* a_begin, int32_t* a_rows, int32_t* b_begin,
                       int32_t* b_cols, int32_t* nsteps_out);
 
+/* [host] the panel broadcasts tadev_summa_f64 issues for `plan` at grid position (r, c), in issue
+ * order: comm[n] = 0 row / 1 column communicator, group[n] = ordinal of the NCCL group the call is
+ * part of, k[n] = SUMMA step, root[n], bytes[n]. Only the host-side fields of the plan are read
+ * (extents, norms, flags, steps_per_launch, row_blocks). NCCL may reorder calls inside a group, so
+ * all ranks of a communicator must produce the same calls in the same groups — checked on the CPU
+ * by tests/test_host_logic.py for every grid position. Pass NULL arrays to query the count. */
+int tadev_summa_comm_trace(int Pr, int Pc, int r, int c, const tadev_summa_plan* plan, int32_t* comm,
+                           int32_t* group, int32_t* k, int32_t* root, int64_t* bytes, int64_t capacity,
+                           int64_t* n_out);
+
 /* ---- measurement helpers -------------------------------------------------------------------
  * Register-resident DMMA / DFMA issue-rate probes: the FP64 roofline denominator is not in
  * MEASURED_PEAKS.json and must be measured on the box. Returns TFLOP/s. */

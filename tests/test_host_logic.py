@@ -189,3 +189,73 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
         assert got[(cname, "size")] == C.sizeof(py), cname
         for fname, _ in py._fields_:
             assert got[(cname, fname)] == getattr(py, fname).offset, (cname, fname)
+
+
+def _comm_trace(lib, Pr, Pc, r, c, m_ext, n_ext, k_ext, a_n, b_n, c_n, flags, spl, row_blocks):
+    import ctypes as C
+    from tiledarray_b200 import _lib as L
+    sp = L.SummaPlanC()
+    sp.Mt, sp.Nt, sp.Kt = len(m_ext), len(n_ext), len(k_ext)
+    keep = [np.asarray(x, dtype=np.int64) for x in (m_ext, n_ext, k_ext)]
+    sp.m_ext, sp.n_ext, sp.k_ext = (x.ctypes.data_as(C.POINTER(C.c_int64)) for x in keep)
+    fp = C.POINTER(C.c_float)
+    if a_n is not None:
+        norms = [np.ascontiguousarray(x, dtype=np.float32) for x in (a_n, b_n, c_n)]
+        keep += norms
+        sp.a_norms, sp.b_norms, sp.c_norms = (x.ctypes.data_as(fp) for x in norms)
+    sp.threshold = 1e-6
+    sp.flags, sp.steps_per_launch, sp.row_blocks = flags, spl, row_blocks
+    n = C.c_int64()
+    L.check(lib.tadev_summa_comm_trace(Pr, Pc, r, c, C.byref(sp), None, None, None, None, None, 0, C.byref(n)))
+    cap = max(n.value, 1)
+    comm, group, k, root = (np.zeros(cap, dtype=np.int32) for _ in range(4))
+    nbytes = np.zeros(cap, dtype=np.int64)
+    L.check(lib.tadev_summa_comm_trace(Pr, Pc, r, c, C.byref(sp), comm.ctypes.data, group.ctypes.data, k.ctypes.data,
+                                       root.ctypes.data, nbytes.ctypes.data, cap, C.byref(n)))
+    return [(int(comm[i]), int(group[i]), int(k[i]), int(root[i]), int(nbytes[i])) for i in range(n.value)]
+
+
+@pytest.mark.parametrize("grid", [(1, 2), (2, 1), (2, 2), (4, 2), (2, 3)])
+@pytest.mark.parametrize("flags", [0, 1 | 2 | 4, 1, 2 | 4, 8])
+@pytest.mark.parametrize("density", [1.0, 0.4, 0.15])
+def test_summa_nccl_groups_agree_across_ranks(lib, grid, flags, density):
+    """Deadlock-freedom of the panel broadcasts, on the CPU: every rank of a row (column) communicator
+    must issue the same broadcasts, in the same order, partitioned into the same NCCL groups (NCCL may
+    reorder the calls of one group), whatever its own sparsity pattern, memory placement of the arrays
+    (flags: host-resident / lazy operands, host-resident result => row blocks) and window size. The
+    first version of the driver cut windows by the rank's own compute steps and hung on 2 GPUs with
+    block-sparse host-resident arrays."""
+    Pr, Pc = grid
+    rng = np.random.default_rng(Pr * 100 + Pc * 10 + flags + int(density * 100))
+    for trial in range(4):
+        Mt, Nt, Kt = (int(x) for x in rng.integers(3, 10, 3))
+        m_ext, n_ext, k_ext = (rng.integers(8, 70, n) * 2 for n in (Mt, Nt, Kt))
+        if density < 1.0:
+            a_n = (rng.random((Mt, Kt)) < density).astype(np.float32)
+            b_n = (rng.random((Kt, Nt)) < density).astype(np.float32)
+            c_n = ((a_n @ b_n) > 0).astype(np.float32)
+        else:
+            a_n = b_n = c_n = None
+        for spl, rb in ((0, 0), (1, 0), (2, 3), (3, 2)):
+            traces = {(r, c): _comm_trace(lib, Pr, Pc, r, c, m_ext, n_ext, k_ext, a_n, b_n, c_n, flags, spl, rb)
+                      for r in range(Pr) for c in range(Pc)}
+
+            def per_comm(t, which):
+                calls = [(k, root, nb, g) for (cm, g, k, root, nb) in t if cm == which]
+                groups, first = [], {}
+                for k, root, nb, g in calls:  # renumber the groups of this communicator 0, 1, 2, ...
+                    groups.append((k, root, nb, first.setdefault(g, len(first))))
+                return groups
+
+            for r in range(Pr):  # row communicator: ranks (r, *)
+                ref = per_comm(traces[(r, 0)], 0)
+                for c in range(1, Pc):
+                    assert per_comm(traces[(r, c)], 0) == ref, (grid, flags, density, trial, spl, rb, "row", r, c)
+            for c in range(Pc):  # column communicator: ranks (*, c)
+                ref = per_comm(traces[(0, c)], 1)
+                for r in range(1, Pr):
+                    assert per_comm(traces[(r, c)], 1) == ref, (grid, flags, density, trial, spl, rb, "col", r, c)
+            # roots follow the cyclic maps and every call moves data
+            for t in traces.values():
+                for cm, g, k, root, nb in t:
+                    assert root == (k % Pc if cm == 0 else k % Pr) and nb > 0

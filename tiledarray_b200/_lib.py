@@ -159,6 +159,7 @@ PROTOTYPES = {
                                   _i64, _P(_i64)]),
     "tadev_summa_steps": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                                _P(C.c_int32)]),
+    "tadev_summa_comm_trace": (_i, [_i, _i, _i, _i, _P(SummaPlanC), _vp, _vp, _vp, _vp, _vp, _i64, _P(_i64)]),
     "tadev_probe_fp64_peak": (_i, [_vp, _i, _i, _P(_d), _P(_f)]),
     "tadev_probe_copy_gbs": (_i, [_vp, _sz, _i, _P(_d)]),
     "tadev_probe_pcie_gbs": (_i, [_vp, _sz, _P(_d), _P(_d), _P(_d), _P(_d)]),

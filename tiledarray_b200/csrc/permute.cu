@@ -327,7 +327,8 @@ int launch_tiled(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const void
   static const int fast_env = getenv("TADEV_PERM_FAST") ? atoi(getenv("TADEV_PERM_FAST")) : 2;  // 0 generic, 1 scalar, 2 vector
   bool ext32 = true;
   for (int d = 0; d < p.R; ++d) ext32 = ext32 && p.ext[d] < (1ll << 31);
-  if (sizeof(T) == 8 && p.TA == 64 && p.TB == 32 && fast_env > 0 && ext32) {
+  const bool fast_shape = (p.TA * p.TB == 2048) && p.TA >= 8 && p.TA <= 256;
+  if (sizeof(T) == 8 && fast_shape && fast_env > 0 && ext32) {
     // 16-byte accesses need every row start 16-byte aligned on both sides: even extents along a and
     // b make all strides even (the other modes' strides are multiples of those extents)
     bool vec = fast_env > 1 && ptrs_al16 && (p.ext[p.a] % 2 == 0) && (p.ext[p.b] % 2 == 0);
@@ -335,8 +336,24 @@ int launch_tiled(tadev_ctx* ctx, cudaStream_t s, const PermParams& p, const void
       if (d != p.a && (p.sin[d] & 1)) vec = false;
       if (d != p.b && (p.sout[d] & 1)) vec = false;
     }
-    if (vec) transpose_fast_kernel<64, 32, true><<<dim3((unsigned)blocks, (unsigned)ntiles), 256, 0, s>>>((const uint64_t*)in, (uint64_t*)out, d_ins, d_outs, p);
-    else transpose_fast_kernel<64, 32, false><<<dim3((unsigned)blocks, (unsigned)ntiles), 256, 0, s>>>((const uint64_t*)in, (uint64_t*)out, d_ins, d_outs, p);
+    const dim3 grid((unsigned)blocks, (unsigned)ntiles);
+    const uint64_t* i8 = (const uint64_t*)in;
+    uint64_t* o8 = (uint64_t*)out;
+#define TADEV_FAST_CASE(TA_, TB_)                                                                        \
+  case TA_:                                                                                              \
+    if (vec) transpose_fast_kernel<TA_, TB_, true><<<grid, 256, 0, s>>>(i8, o8, d_ins, d_outs, p);       \
+    else transpose_fast_kernel<TA_, TB_, false><<<grid, 256, 0, s>>>(i8, o8, d_ins, d_outs, p);         \
+    break;
+    switch (p.TA) {
+      TADEV_FAST_CASE(8, 256)
+      TADEV_FAST_CASE(16, 128)
+      TADEV_FAST_CASE(32, 64)
+      TADEV_FAST_CASE(64, 32)
+      TADEV_FAST_CASE(128, 16)
+      TADEV_FAST_CASE(256, 8)
+      default: break;
+    }
+#undef TADEV_FAST_CASE
     ctx->launches++;
     TADEV_CHECK_CUDA(cudaGetLastError());
     return TADEV_OK;

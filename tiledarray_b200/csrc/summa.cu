@@ -151,45 +151,47 @@ struct Window {
 
 }  // namespace
 
-// -----------------------------------------------------------------------------------------------
-// The driver. Loops: row blocks of the result (1 unless the result lives in host memory) ->
-// windows of K steps -> [H2D staging of host-resident panels | NCCL panel broadcasts] overlapped
-// with ONE grouped GEMM launch per window; finished result blocks are copied to the host while
-// the next block computes. See the file header for the reference mapping.
-extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_stats* stats) {
-  TADEV_REQUIRE(ctx && plan, "tadev_summa_f64: null");
-  const tadev_summa_plan& P = *plan;
-  TADEV_REQUIRE(P.Mt >= 0 && P.Nt >= 0 && P.Kt >= 0, "tadev_summa_f64: negative tile-grid extents");
-  TADEV_REQUIRE((P.opA == 0 || P.opA == 1) && (P.opB == 0 || P.opB == 1), "tadev_summa_f64: bad op flags");
-  TADEV_REQUIRE(P.m_ext && P.n_ext && (P.Kt == 0 || P.k_ext), "tadev_summa_f64: null extent arrays");
-  TADEV_REQUIRE(P.a_tiles && P.b_tiles && P.c_tiles, "tadev_summa_f64: null tile tables");
-  if (stats) memset(stats, 0, sizeof(*stats));
-  const int Pr = ctx->Pr, Pc = ctx->Pc, r = ctx->my_r, c = ctx->my_c;
-  if (r < 0 || c < 0) return TADEV_OK;  // outside the process grid: nothing to do
-  const bool multi = (Pr * Pc > 1);
-  TADEV_REQUIRE(!multi || (ctx->row_comm && ctx->col_comm), "tadev_summa_f64: communicators not initialised");
+namespace {
+
+// Everything the driver derives from the plan before touching the device: the step schedule of this
+// grid position, the row blocks, the B cache decision, and the (block, window) structure. Host-only,
+// shared by tadev_summa_f64 and tadev_summa_comm_trace.
+struct SummaWindows {
+  SummaSchedule S;
+  std::vector<int> my_rows;
+  int nb = 1, W = 1, D = 2;
+  bool b_cache = false;
+  std::vector<std::vector<BlockStep>> bsteps;
+  std::vector<std::vector<Window>> bwins;
+  std::vector<std::pair<int, int>> brange;  // [first, last) positions in my_rows
+  size_t max_bytes = 0, b_cache_elems = 0;
+  std::vector<size_t> b_cache_off;
+};
+
+void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P, SummaWindows& X) {
   const int Mt = P.Mt, Nt = P.Nt, Kt = P.Kt;
+  const bool multi = (Pr * Pc > 1);
   const bool a_host = (P.flags & TADEV_SUMMA_A_ON_HOST) != 0, b_host = (P.flags & TADEV_SUMMA_B_ON_HOST) != 0,
              c_host = (P.flags & TADEV_SUMMA_C_ON_HOST) != 0;
   const bool a_lazy = (P.flags & TADEV_SUMMA_A_LAZY) != 0, b_lazy = (P.flags & TADEV_SUMMA_B_LAZY) != 0;
-  TADEV_REQUIRE(!(a_lazy && a_host) && !(b_lazy && b_host), "tadev_summa_f64: an operand cannot be both lazy and host-resident");
-  TADEV_REQUIRE((!a_lazy || P.a_provider) && (!b_lazy || P.b_provider), "tadev_summa_f64: lazy operand without a tile provider");
-  // "staged" operands have no device-resident tiles: every panel is materialised in the ring (or the
-  // B cache) by an upload or by the provider, on the staging stream
   const bool a_stg = a_host || a_lazy, b_stg = b_host || b_lazy;
-  TADEV_CHECK_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t s0 = ctx->streams[0];                       // compute
-  cudaStream_t sd = ctx->streams[ctx->streams.size() > 1 ? 1 : 0];  // result download
-  cudaStream_t sc = ctx->comm_stream[0];                   // NCCL panel broadcasts
-  cudaStream_t sh = ctx->comm_stream[1];                   // host -> device panel staging
-
-  SummaSchedule S = make_summa_schedule(Pr, Pc, r, c, Mt, Nt, Kt, P.a_norms, P.b_norms, P.c_norms, P.threshold);
+  SummaSchedule& S = X.S;
+  std::vector<int>& my_rows = X.my_rows;
+  int& nb = X.nb;
+  int& W = X.W;
+  bool& b_cache = X.b_cache;
+  auto& bsteps = X.bsteps;
+  auto& bwins = X.bwins;
+  auto& brange = X.brange;
+  size_t& max_bytes = X.max_bytes;
+  size_t& b_cache_elems = X.b_cache_elems;
+  auto& b_cache_off = X.b_cache_off;
+  S = make_summa_schedule(Pr, Pc, r, c, Mt, Nt, Kt, P.a_norms, P.b_norms, P.c_norms, P.threshold);
 
   // ---- row blocks (deterministic from global quantities: every rank must agree on the count
   //      because B panels are re-broadcast per block unless they are cached)
-  std::vector<int> my_rows;
   for (int i = r; i < Mt; i += Pr) my_rows.push_back(i);
-  int nb = 1;
+  nb = 1;
   if (!c_host && (P.row_blocks > 0 || a_lazy)) {
     // device-resident result in row blocks: bounds the A panel of one step when A is generated on
     // the fly (each block needs only its own rows of the panel). Same count on every rank.
@@ -216,7 +218,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   // B staged through the device (received by broadcast or uploaded from the host) is kept for all
   // row blocks when it fits the cache budget; the dense upper bound is the same on every rank.
   const bool b_staged = b_stg || (multi && Pr > 1);
-  bool b_cache = false;
+  b_cache = false;
   if (nb > 1 && b_staged) {
     double k_sum = 0, n_max = 0;
     for (int k = 0; k < Kt; ++k) k_sum += (double)P.k_ext[k];
@@ -226,7 +228,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     b_cache = k_sum * n_max * 8.0 <= limit;
   }
 
-  int W = P.steps_per_launch;
+  W = P.steps_per_launch;
   if (W <= 0) {
     if (!multi && !a_stg && !b_stg) W = std::max(1, Kt);
     else {
@@ -237,16 +239,16 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     }
   }
   const size_t kMaxWindowBytes = size_t(5) << 30;
-  const int D = std::max(2, P.depth > 0 ? P.depth : 2);
+  X.D = std::max(2, P.depth > 0 ? P.depth : 2);
 
   // ---- per-block step views and windows
   auto tile_a_elems = [&](int i, int k) { return (size_t)P.m_ext[i] * (size_t)P.k_ext[k]; };
   auto tile_b_elems = [&](int k, int j) { return (size_t)P.k_ext[k] * (size_t)P.n_ext[j]; };
-  std::vector<std::vector<BlockStep>> bsteps(nb);
-  std::vector<std::vector<Window>> bwins(nb);
-  std::vector<std::pair<int, int>> brange(nb);  // [first, last) positions in my_rows
-  size_t max_bytes = 0, b_cache_elems = 0;
-  std::vector<size_t> b_cache_off(S.steps.size(), 0);
+  bsteps.assign(nb, {});
+  bwins.assign(nb, {});
+  brange.assign(nb, {0, 0});
+  max_bytes = 0; b_cache_elems = 0;
+  b_cache_off.assign(S.steps.size(), 0);
   for (size_t si = 0; si < S.steps.size(); ++si) {
     size_t e = 0;
     for (int j : S.steps[si].b_cols) e += pad2(tile_b_elems(S.steps[si].k, j));
@@ -339,6 +341,85 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     }
     max_bytes = 0;
   }
+
+}
+
+}  // namespace
+
+// [host] the panel broadcasts the driver issues for this plan at grid position (r, c), in issue order
+extern "C" int tadev_summa_comm_trace(int Pr, int Pc, int r, int c, const tadev_summa_plan* plan, int32_t* comm,
+                                      int32_t* group, int32_t* k, int32_t* root, int64_t* bytes, int64_t capacity,
+                                      int64_t* n_out) {
+  TADEV_REQUIRE(plan && n_out, "tadev_summa_comm_trace: null");
+  TADEV_REQUIRE(Pr >= 1 && Pc >= 1 && r >= 0 && r < Pr && c >= 0 && c < Pc, "tadev_summa_comm_trace: bad grid position");
+  TADEV_REQUIRE(plan->m_ext && plan->n_ext && (plan->Kt == 0 || plan->k_ext), "tadev_summa_comm_trace: null extent arrays");
+  SummaWindows X;
+  build_summa_windows(Pr, Pc, r, c, *plan, X);
+  int64_t n = 0;
+  int32_t g = 0;
+  auto emit = [&](int cm, int kk, int rt, size_t by) {
+    if (n < capacity && comm && group && k && root && bytes) { comm[n] = cm; group[n] = g; k[n] = kk; root[n] = rt; bytes[n] = (int64_t)by; }
+    ++n;
+  };
+  for (int b = 0; b < X.nb; ++b)
+    for (const Window& win : X.bwins[b]) {
+      bool any = false;
+      for (int x : win.steps) { const BlockStep& bs = X.bsteps[b][x]; if (bs.bcast_a) { emit(0, bs.st->k, bs.st->k % Pc, bs.a_elems * 8); any = true; } }
+      if (any) ++g;
+      any = false;
+      for (int x : win.steps) { const BlockStep& bs = X.bsteps[b][x]; if (bs.bcast_b) { emit(1, bs.st->k, bs.st->k % Pr, bs.b_elems * 8); any = true; } }
+      if (any) ++g;
+    }
+  *n_out = n;
+  TADEV_REQUIRE(n <= capacity || !comm, "tadev_summa_comm_trace: capacity %lld < %lld", (long long)capacity, (long long)n);
+  return TADEV_OK;
+}
+
+// -----------------------------------------------------------------------------------------------
+// The driver. Loops: row blocks of the result (1 unless the result lives in host memory) ->
+// windows of K steps -> [H2D staging of host-resident panels | NCCL panel broadcasts] overlapped
+// with ONE grouped GEMM launch per window; finished result blocks are copied to the host while
+// the next block computes. See the file header for the reference mapping.
+extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_stats* stats) {
+  TADEV_REQUIRE(ctx && plan, "tadev_summa_f64: null");
+  const tadev_summa_plan& P = *plan;
+  TADEV_REQUIRE(P.Mt >= 0 && P.Nt >= 0 && P.Kt >= 0, "tadev_summa_f64: negative tile-grid extents");
+  TADEV_REQUIRE((P.opA == 0 || P.opA == 1) && (P.opB == 0 || P.opB == 1), "tadev_summa_f64: bad op flags");
+  TADEV_REQUIRE(P.m_ext && P.n_ext && (P.Kt == 0 || P.k_ext), "tadev_summa_f64: null extent arrays");
+  TADEV_REQUIRE(P.a_tiles && P.b_tiles && P.c_tiles, "tadev_summa_f64: null tile tables");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  const int Pr = ctx->Pr, Pc = ctx->Pc, r = ctx->my_r, c = ctx->my_c;
+  if (r < 0 || c < 0) return TADEV_OK;  // outside the process grid: nothing to do
+  const bool multi = (Pr * Pc > 1);
+  TADEV_REQUIRE(!multi || (ctx->row_comm && ctx->col_comm), "tadev_summa_f64: communicators not initialised");
+  const int Mt = P.Mt, Nt = P.Nt, Kt = P.Kt;
+  const bool a_host = (P.flags & TADEV_SUMMA_A_ON_HOST) != 0, b_host = (P.flags & TADEV_SUMMA_B_ON_HOST) != 0,
+             c_host = (P.flags & TADEV_SUMMA_C_ON_HOST) != 0;
+  const bool a_lazy = (P.flags & TADEV_SUMMA_A_LAZY) != 0, b_lazy = (P.flags & TADEV_SUMMA_B_LAZY) != 0;
+  TADEV_REQUIRE(!(a_lazy && a_host) && !(b_lazy && b_host), "tadev_summa_f64: an operand cannot be both lazy and host-resident");
+  TADEV_REQUIRE((!a_lazy || P.a_provider) && (!b_lazy || P.b_provider), "tadev_summa_f64: lazy operand without a tile provider");
+  // "staged" operands have no device-resident tiles: every panel is materialised in the ring (or the
+  // B cache) by an upload or by the provider, on the staging stream
+  const bool a_stg = a_host || a_lazy, b_stg = b_host || b_lazy;
+  TADEV_CHECK_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s0 = ctx->streams[0];                       // compute
+  cudaStream_t sd = ctx->streams[ctx->streams.size() > 1 ? 1 : 0];  // result download
+  cudaStream_t sc = ctx->comm_stream[0];                   // NCCL panel broadcasts
+  cudaStream_t sh = ctx->comm_stream[1];                   // host -> device panel staging
+
+  SummaWindows X;
+  build_summa_windows(Pr, Pc, r, c, P, X);
+  SummaSchedule& S = X.S;
+  const std::vector<int>& my_rows = X.my_rows;
+  const int nb = X.nb, D = X.D;
+  const bool b_cache = X.b_cache;
+  auto& bsteps = X.bsteps;
+  auto& bwins = X.bwins;
+  auto& brange = X.brange;
+  const size_t max_bytes = X.max_bytes, b_cache_elems = X.b_cache_elems;
+  auto& b_cache_off = X.b_cache_off;
+  auto tile_a_elems = [&](int i, int k) { return (size_t)P.m_ext[i] * (size_t)P.k_ext[k]; };
+  auto tile_b_elems = [&](int k, int j) { return (size_t)P.k_ext[k] * (size_t)P.n_ext[j]; };
 
   // ---- resources
   cudaEvent_t ev_start, ev_end, ev_aux;
