@@ -138,6 +138,17 @@ int tadev_scale_f64(tadev_ctx* ctx, tadev_stream s, size_t n, double* d_x, doubl
  * dist_array.h:1553). d_ptrs/d_sizes are device arrays; out is a device array of doubles. */
 int tadev_tile_sqnorms_f64(tadev_ctx* ctx, tadev_stream s, int ntiles, const double* const* d_ptrs,
                            const int64_t* d_sizes, double* d_out);
+/* Batched element-wise tile operations (tile_op/add.h, subt.h, scal.h, mult.h; GPU reference
+ * device/btas_um_tensor.h:377-470 and device/kernel/thrust/mult_kernel.h): for every tile t
+ *   TADEV_EW_AXPBY: out[t] = alpha * x[t] + beta * y[t]      (add, subt, scale, copy)
+ *   TADEV_EW_MULT:  out[t] = alpha * x[t] .* y[t]             (Hadamard product)
+ * h_* are HOST arrays of device pointers / element counts; a NULL x or y entry is a zero tile (block-
+ * sparse operands whose tile is absent); out may alias x or y. One launch for all tiles. */
+#define TADEV_EW_AXPBY 0
+#define TADEV_EW_MULT 1
+int tadev_tiles_binary_f64(tadev_ctx* ctx, tadev_stream s, int op, int ntiles, double* const* h_out,
+                           const double* const* h_x, const double* const* h_y, const int64_t* h_elems,
+                           double alpha, double beta);
 /* counter-based uniform(-1,1) fill keyed by (seed, global element offset): synthetic inputs
  *  and on-the-fly tile generation for tensors that do not fit in HBM. */
 int tadev_fill_uniform_f64(tadev_ctx* ctx, tadev_stream s, double* d_x, size_t n, uint64_t seed,

@@ -292,6 +292,44 @@ class SparseShape:
         out[hit] = 0
         return SparseShape(out, self.size_vectors, self.zero_tile_count + int(hit.sum()), self.threshold)
 
+    def scale(self, factor: float) -> "SparseShape":
+        """scale (sparse_shape.h:1243-1262): value *= |factor|; hard zero below my_threshold."""
+        out = (self.norms * f32(abs(factor))).astype(f32)
+        z = out < f32(self.threshold)
+        out[z] = 0
+        return SparseShape(out, self.size_vectors, int(z.sum()), self.threshold)
+
+    def add(self, other: "SparseShape", factor: Optional[float] = None) -> "SparseShape":
+        """add / subt (sparse_shape.h:1309-1331, 1370-1391, 1499): left += right [; left *= |factor|];
+        hard zero below the global threshold."""
+        assert self.norms.shape == other.norms.shape
+        out = (self.norms + other.norms).astype(f32)
+        if factor is not None:
+            out = (out * f32(abs(factor))).astype(f32)
+        z = out < f32(self.threshold)
+        out[z] = 0
+        return SparseShape(out, self.size_vectors, int(z.sum()), self.threshold)
+
+    def mult(self, other: "SparseShape", factor: Optional[float] = None) -> "SparseShape":
+        """mult (sparse_shape.h:1522-1563): tile_norms.mult(other[, |factor|]) then
+        scale_tile_norms<ScaleBy::Volume> (:149-217: rank 1 norm *= size; else norm *= x*y with the
+        non-inverted recursive outer products), screened."""
+        assert self.norms.shape == other.norms.shape
+        out = (self.norms * other.norms).astype(f32)
+        if factor is not None:
+            out = (out * f32(abs(factor))).astype(f32)
+        dim = len(self.size_vectors)
+        if dim == 1:
+            out = (out.ravel() * np.asarray(self.size_vectors[0], dtype=f32)).astype(f32)
+        else:
+            middle = (dim >> 1) + (dim & 1)
+            xy = np.multiply.outer(_recursive_outer_product(self.size_vectors[:middle], False),
+                                   _recursive_outer_product(self.size_vectors[middle:], False)).astype(f32).ravel()
+            out = (out.ravel() * xy).astype(f32)
+        z = out < f32(self.threshold)
+        out[z] = 0
+        return SparseShape(out.reshape(self.norms.shape), self.size_vectors, int(z.sum()), self.threshold)
+
     def gemm(self, other: "SparseShape", factor: float, helper: GemmHelper,
              perm: Optional[Sequence[int]] = None, threshold: Optional[float] = None) -> "SparseShape":
         """gemm (sparse_shape.h:1589-1681) [+ .perm(perm), :1687-1691].

@@ -260,6 +260,82 @@ def test_cont_accumulate(world):
         x.release()
 
 
+def test_elementwise_expressions_dense(world):
+    """AddEngine / SubtEngine / ScalEngine / Hadamard MultEngine on device tiles (tests/expressions_impl.h
+    add, subt, scale, mult, permute blocks): one batched launch per expression; operands in a different
+    index order are permuted first. Exact on integer data."""
+    rng = np.random.default_rng(77)
+    d1, d2 = TiledRange1(0, 3, 10, 16), TiledRange1(0, 5, 8, 21)
+    a, A = _dense_array(world, _tr(d1, d2), rng, True)
+    b, B = _dense_array(world, _tr(d1, d2), rng, True)
+    bt, BT = _dense_array(world, _tr(d2, d1), rng, True)
+    c = DistArray(world, _tr(d1, d2))
+    c["i,j"] = a["i,j"] + b["i,j"]
+    assert np.array_equal(c.to_numpy(), A + B)
+    c["i,j"] = a["i,j"] - b["i,j"]
+    assert np.array_equal(c.to_numpy(), A - B)
+    c["i,j"] = 2.0 * a["i,j"] + 3.0 * bt["j,i"]
+    assert np.array_equal(c.to_numpy(), 2 * A + 3 * BT.T)
+    c["i,j"] = -(a["i,j"] - 2.0 * b["i,j"])
+    assert np.array_equal(c.to_numpy(), -(A - 2 * B))
+    c["i,j"] = a["i,j"] * b["i,j"]  # Hadamard: every index shared and kept
+    assert np.array_equal(c.to_numpy(), A * B)
+    c["i,j"] = 0.5 * (a["i,j"] * bt["j,i"])
+    assert np.array_equal(c.to_numpy(), 0.5 * A * BT.T)
+    c["i,j"] = 4.0 * a["i,j"]
+    assert np.array_equal(c.to_numpy(), 4 * A)
+    ct = DistArray(world, _tr(d2, d1))
+    ct["j,i"] = a["i,j"]  # pure permutation
+    assert np.array_equal(ct.to_numpy(), A.T)
+    c["i,j"] = c["i,j"] + a["i,j"]  # the result is also an operand
+    assert np.array_equal(c.to_numpy(), 5 * A)
+    x, X = _dense_array(world, _tr(d1, d2, d1), rng, True)
+    y, Y = _dense_array(world, _tr(d1, d1, d2), rng, True)
+    z = DistArray(world, _tr(d2, d1, d1))
+    z["b,a,c"] = x["a,b,c"] - 2.0 * y["c,a,b"]
+    assert np.array_equal(z.to_numpy(), np.einsum("abc->bac", X) - 2 * np.einsum("cab->bac", Y))
+    for t in (a, b, bt, c, ct, x, y, z):
+        t.release()
+
+
+def test_elementwise_expressions_sparse_and_truncate(world):
+    """Block-sparse add / subt / Hadamard: result shapes by SparseShape::add / mult (bit-exact vs the oracle),
+    absent tiles act as zeros, result tiles exist exactly where the result shape is non-zero; truncate()
+    recomputes the shape from the true norms (dist_array.h:1553) and drops tiles that cancelled."""
+    rng = np.random.default_rng(13)
+    d = TiledRange1(0, 4, 8, 14, 20)
+    tr = _tr(d, d)
+    (a, A, nA), (b, B, nB) = _sparse_pair(world, tr, tr, 0.5, rng)
+    otr = O.TiledRange((O.TiledRange1(d.bounds), O.TiledRange1(d.bounds)))
+    oa, ob = O.SparseShape.from_tile_norms(nA, otr), O.SparseShape.from_tile_norms(nB, otr)
+    c = DistArray(world, tr)
+    c["i,j"] = a["i,j"] + b["i,j"]
+    assert np.array_equal(c.shape.norms.view(np.uint32), oa.add(ob).norms.view(np.uint32))
+    assert np.array_equal(c.to_numpy(), A + B)
+    assert sorted(c.tiles) == [o for o in range(tr.ntiles) if not c.shape.is_zero(o)]
+    c["i,j"] = 2.0 * a["i,j"] - 0.5 * b["i,j"]
+    assert np.array_equal(c.shape.norms.view(np.uint32), oa.scale(2.0).add(ob.scale(0.5)).norms.view(np.uint32))
+    assert np.array_equal(c.to_numpy(), 2 * A - 0.5 * B)
+    c["i,j"] = 3.0 * (a["i,j"] * b["i,j"])
+    assert np.array_equal(c.shape.norms.view(np.uint32), oa.mult(ob, 3.0).norms.view(np.uint32))
+    assert np.array_equal(c.to_numpy(), 3 * A * B)
+    assert c.shape.zero_tile_count == oa.mult(ob, 3.0).zero_tile_count
+    # a - a: the estimated shape keeps every tile of a, truncate() finds that they are all zero
+    c["i,j"] = a["i,j"] - a["i,j"]
+    assert len(c.tiles) == len(a.tiles) and not c.to_numpy().any()
+    c.truncate()
+    assert len(c.tiles) == 0 and c.shape.zero_tile_count == tr.ntiles
+    # truncate on real data reproduces the shape built from the true norms
+    c["i,j"] = a["i,j"] + b["i,j"]
+    c.truncate()
+    want = O.SparseShape.from_tile_norms(np.array([[np.linalg.norm((A + B)[tr.tile_slices((i, j))]) for j in range(4)]
+                                                   for i in range(4)], dtype=np.float32), otr)
+    np.testing.assert_allclose(c.shape.norms, want.norms, rtol=1e-6)
+    assert (c.shape.norms == 0).tolist() == (want.norms == 0).tolist()
+    for t in (a, b, c):
+        t.release()
+
+
 def test_cont_errors(world):
     t, u = _uniform(8, 4), _uniform(8, 2)
     a = DistArray(world, _tr(t, t)).fill(1.0)

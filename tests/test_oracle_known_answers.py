@@ -138,6 +138,37 @@ def test_sparse_shape_gemm_reference_formula(seed):
     assert abs(res.sparsity() - nz / float(m * n)) < 1e-6
 
 
+@pytest.mark.parametrize("seed", [5, 61])
+def test_sparse_shape_scale_add_mult_reference_formulas(seed):
+    """tests/sparse_shape.cpp:763-834 (scale), :836-915 (add, add_scale; subt == add, sparse_shape.h:1499),
+    :1320-1395 (mult, mult_scale): expected values are the reference tests' own formulas, tolerance
+    1e-4 % (BOOST_CHECK_CLOSE), zero decisions and zero counts exact."""
+    tr = _fixture_trange()
+    rng = np.random.default_rng(seed)
+    ext = [d.extents for d in tr.dims]
+    thr = KA.SPARSE_FIXTURE_THRESHOLD
+    left = O.SparseShape.from_tile_norms(KA.fixture_norms(rng, tr.tiles_shape, ext, 0.3, thr), tr, thr)
+    right = O.SparseShape.from_tile_norms(KA.fixture_norms(rng, tr.tiles_shape, ext, 0.3, thr), tr, thr)
+    vol = np.empty(tr.tiles_shape, dtype=np.float64)
+    for idx in np.ndindex(*tr.tiles_shape):
+        vol[idx] = np.prod(tr.tile_extent(idx))
+    L, R = left.norms.astype(np.float64), right.norms.astype(np.float64)
+    cases = [(left.scale(-4.1), L * 4.1), (left.add(right), L + R), (left.add(right, -7.2), (L + R) * 7.2),
+             (left.mult(right), L * R * vol), (left.mult(right, 2.5), L * R * 2.5 * vol)]
+    for res, expected in cases:
+        expected = np.where(expected < thr, 0.0, expected)
+        nz = 0
+        for idx in np.ndindex(*tr.tiles_shape):
+            got = float(res.norms[idx])
+            assert got == pytest.approx(expected[idx], rel=1e-5, abs=1e-12)
+            if got < thr:
+                assert res.is_zero(idx)
+                nz += 1
+            else:
+                assert not res.is_zero(idx)
+        assert res.zero_tile_count == nz
+
+
 def test_sparse_shape_gemm_c_and_numpy_oracles_bit_identical():
     """The oracle's fixed fp32 order is stated twice (numpy, C with -ffp-contract=off); the two
     statements must agree bit for bit — this is the spec the CUDA screening kernel is held to."""

@@ -61,6 +61,7 @@ SUMMA_A_ON_HOST, SUMMA_B_ON_HOST, SUMMA_C_ON_HOST, SUMMA_A_LAZY, SUMMA_B_LAZY = 
 
 
 MEM_DEVICE, MEM_HOST, MEM_LAZY = 0, 1, 2
+EW_AXPBY, EW_MULT = 0, 1
 
 
 class ArrayDescC(C.Structure):
@@ -132,6 +133,7 @@ PROTOTYPES = {
     "tadev_add_to_f64": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "tadev_scale_f64": (_i, [_vp, _vp, _sz, _vp, _d]),
     "tadev_tile_sqnorms_f64": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "tadev_tiles_binary_f64": (_i, [_vp, _vp, _i, _i, _P(_vp), _P(_vp), _P(_vp), _P(_i64), _d, _d]),
     "tadev_fill_uniform_f64": (_i, [_vp, _vp, _vp, _sz, _u64, _u64]),
     "tadev_shape_scale_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _f, _vp]),
     "tadev_shape_gemm_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp]),

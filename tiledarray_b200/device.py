@@ -213,6 +213,32 @@ class Device:
         check(self.lib.tadev_permute_batched(self.ctx, stream or self.stream, rank, ext, pm, elem_bytes, n,
                                              ins.ctypes.data_as(vpp), outs.ctypes.data_as(vpp)))
 
+    def tiles_binary(self, op: int, out_ptrs: np.ndarray, x_ptrs: np.ndarray, y_ptrs: np.ndarray, elems: np.ndarray,
+                     alpha: float, beta: float, stream=None) -> None:
+        """tadev_tiles_binary_f64 on arrays of raw device pointers (0 = zero tile)."""
+        n = len(out_ptrs)
+        vpp, ip = C.POINTER(C.c_void_p), C.POINTER(C.c_int64)
+        o = np.ascontiguousarray(out_ptrs, dtype=np.uint64)
+        x = np.ascontiguousarray(x_ptrs, dtype=np.uint64)
+        y = np.ascontiguousarray(y_ptrs, dtype=np.uint64)
+        e = np.ascontiguousarray(elems, dtype=np.int64)
+        check(self.lib.tadev_tiles_binary_f64(self.ctx, stream or self.stream, op, n, o.ctypes.data_as(vpp), x.ctypes.data_as(vpp),
+                                              y.ctypes.data_as(vpp), e.ctypes.data_as(ip), alpha, beta))
+
+    def tile_sqnorms(self, ptrs: np.ndarray, elems: np.ndarray, stream=None) -> np.ndarray:
+        """Squared Frobenius norms of tiles given by raw device pointers (tadev_tile_sqnorms_f64)."""
+        n = len(ptrs)
+        if n == 0:
+            return np.zeros(0)
+        d_p = self.upload(np.ascontiguousarray(ptrs, dtype=np.uint64), stream)
+        d_s = self.upload(np.ascontiguousarray(elems, dtype=np.int64), stream)
+        d_o = self.alloc(8 * n, stream)
+        check(self.lib.tadev_tile_sqnorms_f64(self.ctx, stream or self.stream, n, d_p.ptr, d_s.ptr, d_o.ptr))
+        out = self.download(d_o, np.float64, (n,), stream)
+        for b in (d_p, d_s, d_o):
+            b.free()
+        return out
+
     def add_to(self, n: int, result: DeviceBuffer, arg: DeviceBuffer, stream=None) -> None:
         check(self.lib.tadev_add_to_f64(self.ctx, stream or self.stream, n, result.ptr, arg.ptr))
 

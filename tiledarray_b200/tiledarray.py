@@ -260,6 +260,41 @@ class SparseShape:
         res = SparseShape(self.world, None, None, _prebuilt=(out.reshape(res_ext), res_sv, nz, thr))
         return res.perm(perm) if perm is not None else res
 
+    def _with(self, norms: np.ndarray, nzero: int) -> "SparseShape":
+        return SparseShape(self.world, None, None, _prebuilt=(norms.astype(f32), self.size_vectors, int(nzero), self.my_threshold))
+
+    def scale(self, factor: float) -> "SparseShape":
+        """SparseShape::scale (sparse_shape.h:1243): norm * |factor|, hard zero below the threshold."""
+        out = (self.norms * f32(abs(factor))).astype(f32)
+        z = out < f32(self.my_threshold)
+        return self._with(np.where(z, f32(0), out), z.sum())
+
+    def add(self, other: "SparseShape", factor: float = 1.0) -> "SparseShape":
+        """SparseShape::add / subt (sparse_shape.h:1309,1370,1499): (a + b) * |factor|, thresholded."""
+        _ta_assert(self.norms.shape == other.norms.shape, "SparseShape::add: range mismatch")
+        out = (self.norms + other.norms).astype(f32)
+        if factor != 1.0:
+            out = (out * f32(abs(factor))).astype(f32)
+        z = out < f32(SparseShape._threshold)
+        return self._with(np.where(z, f32(0), out), z.sum())
+
+    def mult(self, other: "SparseShape", factor: float = 1.0) -> "SparseShape":
+        """SparseShape::mult (sparse_shape.h:1522,1551): a * b (* |factor|), then scaled by the tile volume
+        (scale_tile_norms<ScaleBy::Volume>, :149-217; on the device) and thresholded."""
+        _ta_assert(self.norms.shape == other.norms.shape, "SparseShape::mult: range mismatch")
+        prod = (self.norms * other.norms).astype(f32)
+        if factor != 1.0:
+            prod = (prod * f32(abs(factor))).astype(f32)
+        dim = len(self.size_vectors)
+        if dim == 1:
+            left, right = self.size_vectors[0], np.ones(1, dtype=f32)
+        else:
+            middle = (dim >> 1) + (dim & 1)
+            left = _recursive_outer(self.size_vectors[:middle], False)
+            right = _recursive_outer(self.size_vectors[middle:], False)
+        out, nz = self.world.dev.shape_scale(prod, left, right, SparseShape._threshold)
+        return self._with(out, nz)
+
     def mask(self, mask_shape: "SparseShape") -> "SparseShape":
         _ta_assert(self.norms.shape == mask_shape.norms.shape, "SparseShape::mask: range mismatch")
         hit = (self.norms >= f32(self.my_threshold)) & (mask_shape.norms < f32(mask_shape.my_threshold))
@@ -414,6 +449,37 @@ class DistArray:
             out[self.trange.tile_slices(self.trange.tile_index(o))] = self.find(o)
         return out
 
+    def tile_norms(self) -> np.ndarray:
+        """Frobenius norms of the local tiles over the tile grid (zeros elsewhere), computed on the device."""
+        _ta_assert(self.memory == "device", "tile_norms: device-resident arrays only")
+        out = np.zeros(max(self.trange.ntiles, 1), dtype=np.float64)
+        if self.tiles:
+            ords = np.fromiter(self.tiles.keys(), dtype=np.int64, count=len(self.tiles))
+            ptrs = np.fromiter((b.ptr for b in self.tiles.values()), dtype=np.uint64, count=len(self.tiles))
+            elems = np.fromiter((b.nbytes // 8 for b in self.tiles.values()), dtype=np.int64, count=len(self.tiles))
+            out[ords] = np.sqrt(self.world.dev.tile_sqnorms(ptrs, elems))
+        return out.reshape(self.trange.tiles_shape)
+
+    def truncate(self) -> "DistArray":
+        """DistArray::truncate (dist_array.h:1553, conversions/truncate.h): recompute the shape from the
+        true tile norms and drop the tiles that fall below the threshold. Dense arrays are unchanged."""
+        if self.shape.is_dense():
+            return self
+        norms = self.tile_norms().astype(f32)
+        if self.world.size > 1:  # shapes are replicated: every rank needs every tile's norm (gop.max, sparse_shape.h:416)
+            import torch
+            import torch.distributed as dist
+            t = torch.from_numpy(norms.copy())
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            norms = t.cpu().numpy()
+        new_shape = SparseShape(self.world, norms, self.trange)
+        for o in [o for o in self.tiles if new_shape.is_zero(o)]:
+            del self.tiles[o]  # views into the arena: the memory is reclaimed with the arena
+        self.shape = new_shape
+        return self
+
     def release(self) -> None:
         if self._arena is not None:
             self._arena.free()
@@ -452,6 +518,15 @@ class Expr:
         _ta_assert(isinstance(other, (int, float)), "unsupported operand")
         return ScalExpr(self, float(other))
 
+    def __add__(self, other):
+        return AddExpr(self, other, 1.0)
+
+    def __sub__(self, other):
+        return AddExpr(self, other, -1.0)
+
+    def __neg__(self):
+        return ScalExpr(self, -1.0)
+
 
 class TsrExpr(Expr):
     def __init__(self, array: DistArray, indices: List[str]):
@@ -464,14 +539,30 @@ class TsrExpr(Expr):
         return _ASSIGNED
 
     def assign(self, expr, accumulate: bool = False) -> None:
-        factor = 1.0
-        while isinstance(expr, ScalExpr):
-            factor *= expr.scalar
-            expr = expr.arg
-        _ta_assert(isinstance(expr, MultExpr), "only contraction expressions are implemented (SURVEY §8)")
-        _ta_assert(isinstance(expr.left, TsrExpr) and isinstance(expr.right, TsrExpr),
-                   "contraction operands must be arrays (nested expressions are out of scope)")
-        ContEngine(self, expr.left, expr.right, factor, accumulate).eval()
+        factor, expr = _peel(expr)
+        if isinstance(expr, MultExpr):
+            fl, left = _peel(expr.left)
+            fr, right = _peel(expr.right)
+            _ta_assert(isinstance(left, TsrExpr) and isinstance(right, TsrExpr),
+                       "product operands must be (scaled) arrays (nested expressions are out of scope)")
+            factor *= fl * fr
+            if set(left.indices) == set(right.indices) == set(self.indices):
+                # every index is shared and kept: Hadamard product (mult_engine.h), no contraction
+                _ta_assert(not accumulate, "+= of a Hadamard product is not implemented")
+                ElementwiseEngine(self, _lib.EW_MULT, factor, left, 1.0, right).eval()
+            else:
+                ContEngine(self, left, right, factor, accumulate).eval()
+            return
+        _ta_assert(not accumulate, "+= is implemented for contractions only")
+        if isinstance(expr, AddExpr):
+            fl, left = _peel(expr.left)
+            fr, right = _peel(expr.right)
+            _ta_assert(isinstance(left, TsrExpr) and isinstance(right, TsrExpr),
+                       "sum operands must be (scaled) arrays (nested expressions are out of scope)")
+            ElementwiseEngine(self, _lib.EW_AXPBY, factor * fl, left, factor * fr * expr.sign, right).eval()
+            return
+        _ta_assert(isinstance(expr, TsrExpr), "unsupported expression")
+        ElementwiseEngine(self, _lib.EW_AXPBY, factor, expr, 0.0, None).eval()  # c(idx) = f * a(idx'): scale / copy / permute
 
 
 class ScalExpr(Expr):
@@ -482,6 +573,20 @@ class ScalExpr(Expr):
 class MultExpr(Expr):
     def __init__(self, left, right):
         self.left, self.right = left, right
+
+
+class AddExpr(Expr):
+    def __init__(self, left, right, sign: float):
+        self.left, self.right, self.sign = left, right, sign
+
+
+def _peel(expr):
+    """(accumulated scalar factor, inner expression) of nested ScalExpr nodes."""
+    factor = 1.0
+    while isinstance(expr, ScalExpr):
+        factor *= expr.scalar
+        expr = expr.arg
+    return factor, expr
 
 
 # ---------------------------------------------------------------------------------------------
@@ -500,6 +605,102 @@ class ContractionStats:
     row_blocks: int = 1
     lazy_tiles: int = 0
     swapped: bool = False
+
+
+class ElementwiseEngine:
+    """c(idx) = alpha * a(idx_a) (+ beta * b(idx_b) | .* b(idx_b)): the reference's AddEngine / SubtEngine /
+    ScalEngine / MultEngine-Hadamard (expressions/add_engine.h, subt_engine.h, scal_engine.h, mult_engine.h)
+    for device arrays. Operands whose index order differs from the target are permuted first (one batched
+    tadev_permute_batched launch per tile extent); then ONE tadev_tiles_binary_f64 launch produces every
+    result tile. Result shape: SparseShape::scale / add / mult."""
+
+    last_ms: float = 0.0
+
+    def __init__(self, result: "TsrExpr", op: int, alpha: float, a: "TsrExpr", beta: float, b: Optional["TsrExpr"]):
+        self.result, self.op, self.alpha, self.a, self.beta, self.b = result, op, alpha, a, beta, b
+        self.world = a.array.world
+        self.dev = self.world.dev
+
+    def _aligned(self, leaf: "TsrExpr"):
+        """(trange, shape, {ordinal: ptr}, temp arena or None) of the operand in TARGET index order."""
+        arr, tgt = leaf.array, self.result.indices
+        _ta_assert(arr.memory == "device", "element-wise expressions: device-resident arrays only")
+        _ta_assert(sorted(leaf.indices) == sorted(tgt), f"indices {leaf.indices} do not match the target {tgt}")
+        arr._allocate()
+        if leaf.indices == tgt:
+            return arr.trange, arr.shape, {o: b.ptr for o, b in arr.tiles.items()}, None
+        perm = [tgt.index(x) for x in leaf.indices]  # image form: result[perm[i]] = arg[i]
+        rank = len(perm)
+        dims = [None] * rank
+        for i, p in enumerate(perm):
+            dims[p] = arr.trange.dims[i]
+        tr = TiledRange(dims)
+        shape = arr.shape.perm(perm) if not arr.shape.is_dense() else arr.shape
+        ords = np.fromiter(arr.tiles.keys(), dtype=np.int64, count=len(arr.tiles))
+        ptrs = np.fromiter((b_.ptr for b_ in arr.tiles.values()), dtype=np.uint64, count=len(arr.tiles))
+        if not len(ords):
+            return tr, shape, {}, None
+        idx = np.stack(np.unravel_index(ords, arr.trange.tiles_shape), axis=1)
+        ext = np.stack([np.asarray(d.extents, dtype=np.int64)[idx[:, a_]] for a_, d in enumerate(arr.trange.dims)], axis=1)
+        pidx = np.empty_like(idx)
+        pidx[:, perm] = idx
+        pords = np.ravel_multi_index(tuple(pidx.T), tr.tiles_shape).astype(np.int64)
+        elems = ext.prod(axis=1)
+        offs = np.concatenate([[0], np.cumsum((elems + 1) & ~1)]).astype(np.int64)
+        arena = self.dev.alloc(max(int(offs[-1]), 2) * 8)
+        dst = (arena.ptr + offs[:-1] * 8).astype(np.uint64)
+        uniq, inv = np.unique(ext, axis=0, return_inverse=True)
+        inv = inv.ravel()
+        for u in range(len(uniq)):
+            sel = np.nonzero(inv == u)[0]
+            self.dev.permute_batched_ptrs(tuple(int(x) for x in uniq[u]), perm, 8, ptrs[sel], dst[sel])
+        return tr, shape, dict(zip(pords.tolist(), dst.tolist())), arena
+
+    def eval(self) -> None:
+        dev, w = self.dev, self.world
+        Cres = self.result.array
+        _ta_assert(Cres.memory == "device", "element-wise expressions: device-resident result only")
+        with dev.timer() as tm:
+            trA, shA, tA, tmpA = self._aligned(self.a)
+            if self.b is not None:
+                trB, shB, tB, tmpB = self._aligned(self.b)
+                _ta_assert(trA == trB, "element-wise expression: operand tilings differ")
+                _ta_assert(shA.is_dense() == shB.is_dense(), "mixed dense/sparse element-wise expression is not supported")
+            else:
+                trB, shB, tB, tmpB = trA, shA, {}, None
+            # result shape (leaf scaling first, like ScalTsrExpr feeding Add/MultEngine)
+            if shA.is_dense():
+                shape = DenseShape()
+            elif self.b is None:
+                shape = shA.scale(self.alpha)
+            elif self.op == _lib.EW_MULT:
+                shape = shA.mult(shB, self.alpha)
+            else:
+                shape = shA.scale(self.alpha).add(shB.scale(self.beta))
+            r = w.rank
+            own = self.a.array._owner if self.a.indices == self.result.indices else (lambda o: 0)
+            _ta_assert(w.size == 1 or self.a.indices == self.result.indices,
+                       "multi-rank element-wise expressions need operands in the target's index order (no redistribution)")
+            ords = [o for o in range(trA.ntiles) if own(o) == r and not shape.is_zero(o)]
+            elems = np.asarray([int(np.prod(trA.tile_extent(trA.tile_index(o)), dtype=np.int64)) for o in ords], dtype=np.int64)
+            offs = np.concatenate([[0], np.cumsum((elems + 1) & ~1)]).astype(np.int64)
+            arena = dev.alloc(max(int(offs[-1]), 2) * 8)
+            out = (arena.ptr + offs[:-1] * 8).astype(np.uint64)
+            x = np.asarray([tA.get(o, 0) for o in ords], dtype=np.uint64)
+            y = np.asarray([tB.get(o, 0) for o in ords], dtype=np.uint64)
+            if len(ords):
+                dev.tiles_binary(self.op, out, x, y, elems, self.alpha, self.beta)
+            for t in (tmpA, tmpB):
+                if t is not None:
+                    t.free()
+        ElementwiseEngine.last_ms = tm.ms
+        if Cres is not self.a.array and (self.b is None or Cres is not self.b.array):
+            Cres.release()
+        else:  # c = c + b: the old tiles were operands; drop them now
+            Cres.release()
+        Cres.trange, Cres.shape, Cres._arena = trA, shape, arena
+        Cres.tiles = {o: DeviceBuffer(dev, int(p), int(e) * 8, False) for o, p, e in zip(ords, out.tolist(), elems.tolist())}
+        Cres._owner = own
 
 
 class _Contraction:
