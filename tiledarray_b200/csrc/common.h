@@ -40,6 +40,7 @@ struct StagingRing {
   void* d[kSlots] = {nullptr, nullptr, nullptr, nullptr};
   size_t cap[kSlots] = {0, 0, 0, 0};
   cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t uploaded[kSlots] = {nullptr, nullptr, nullptr, nullptr};
   int next = 0;
 };
 
@@ -49,6 +50,7 @@ struct tadev_ctx {
   cudaMemPool_t pool = nullptr;
   std::vector<cudaStream_t> streams;  // compute streams (non-blocking)
   cudaStream_t comm_stream[2] = {nullptr, nullptr};  // row / column panel broadcasts (high priority)
+  cudaStream_t desc_stream = nullptr;  // descriptor uploads: never queued behind a caller stream's pending work
   std::atomic<int64_t> launches{0};
   std::mutex mu;  // guards staging rings
   std::vector<std::pair<cudaStream_t, StagingRing>> staging;
@@ -65,7 +67,13 @@ struct tadev_ctx {
 
 // Obtain a staging slot of at least `bytes` for stream s. Returns host + device pointers; the
 // caller memcpyAsync's h->d on s and then records `*done` on s after the consuming kernel.
-int tadev_stage(tadev_ctx* ctx, cudaStream_t s, size_t bytes, void** h, void** d, cudaEvent_t* done);
+int tadev_stage(tadev_ctx* ctx, cudaStream_t s, size_t bytes, void** h, void** d, cudaEvent_t* done,
+                cudaEvent_t* uploaded = nullptr);
+// Upload a staged descriptor block on the ctx's descriptor stream and make `s` wait for it. Enqueued
+// on `s` itself the copy would only be issued when the previous kernel of `s` finishes — the moment the
+// SUMMA driver's next multi-GB panel upload grabs the H2D copy engine — and the next GEMM would start a
+// whole panel-copy late (measured: 25 ms per window with host-resident operands).
+int tadev_stage_upload(tadev_ctx* ctx, cudaStream_t s, void* d, const void* h, size_t bytes, cudaEvent_t uploaded);
 
 // kernels' internal launchers (device-resident descriptors)
 int launch_gemm_grouped_f64(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, double alpha,

@@ -55,6 +55,7 @@ extern "C" int tadev_init(int device, size_t pool_bytes, tadev_ctx** out) {
     TADEV_CHECK_CUDA(cudaStreamCreateWithPriority(&ctx->streams[i], cudaStreamNonBlocking, lo));
   for (int i = 0; i < 2; ++i)
     TADEV_CHECK_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream[i], cudaStreamNonBlocking, hi));
+  TADEV_CHECK_CUDA(cudaStreamCreateWithPriority(&ctx->desc_stream, cudaStreamNonBlocking, hi));
   *out = ctx;
   return TADEV_OK;
 }
@@ -70,11 +71,13 @@ extern "C" int tadev_finalize(tadev_ctx* ctx) {
       if (pr.second.h[i]) cudaFreeHost(pr.second.h[i]);
       if (pr.second.d[i]) cudaFree(pr.second.d[i]);
       if (pr.second.done[i]) cudaEventDestroy(pr.second.done[i]);
+      if (pr.second.uploaded[i]) cudaEventDestroy(pr.second.uploaded[i]);
     }
   }
   for (auto s : ctx->streams) cudaStreamDestroy(s);
   for (int i = 0; i < 2; ++i)
     if (ctx->comm_stream[i]) cudaStreamDestroy(ctx->comm_stream[i]);
+  if (ctx->desc_stream) cudaStreamDestroy(ctx->desc_stream);
   delete ctx;
   return TADEV_OK;
 }
@@ -176,7 +179,14 @@ extern "C" int tadev_launch_count(tadev_ctx* ctx, int64_t* n) {
   return TADEV_OK;
 }
 
-int tadev_stage(tadev_ctx* ctx, cudaStream_t s, size_t bytes, void** h, void** d, cudaEvent_t* done) {
+int tadev_stage_upload(tadev_ctx* ctx, cudaStream_t s, void* d, const void* h, size_t bytes, cudaEvent_t uploaded) {
+  TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->desc_stream));
+  TADEV_CHECK_CUDA(cudaEventRecord(uploaded, ctx->desc_stream));
+  TADEV_CHECK_CUDA(cudaStreamWaitEvent(s, uploaded, 0));
+  return TADEV_OK;
+}
+
+int tadev_stage(tadev_ctx* ctx, cudaStream_t s, size_t bytes, void** h, void** d, cudaEvent_t* done, cudaEvent_t* uploaded) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   StagingRing* ring = nullptr;
   for (auto& pr : ctx->staging)
@@ -197,8 +207,10 @@ int tadev_stage(tadev_ctx* ctx, cudaStream_t s, size_t bytes, void** h, void** d
     TADEV_CHECK_CUDA(cudaMalloc(&ring->d[i], cap));
     ring->cap[i] = cap;
   }
+  if (!ring->uploaded[i]) TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&ring->uploaded[i], cudaEventDisableTiming));
   *h = ring->h[i];
   *d = ring->d[i];
   *done = ring->done[i];
+  if (uploaded) *uploaded = ring->uploaded[i];
   return TADEV_OK;
 }

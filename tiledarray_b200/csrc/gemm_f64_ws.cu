@@ -594,8 +594,8 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
   const size_t off_p = (off_t + tb + 15) & ~size_t(15);
   const size_t off_c = (off_p + pb + 15) & ~size_t(15);
   void *h = nullptr, *d = nullptr;
-  cudaEvent_t done;
-  int rc = tadev_stage(ctx, s, off_c + 16, &h, &d, &done);
+  cudaEvent_t done, uploaded;
+  int rc = tadev_stage(ctx, s, off_c + 16, &h, &d, &done, &uploaded);
   if (rc) return rc;
   memcpy(h, h_groups, gb);
   rc = resolve_maps(ctx, opA, opB, h_groups, ngroups, h_tasks, (WsTask*)((char*)h + off_t));
@@ -622,7 +622,8 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
     wave_sync = uniform ? 1 : 0;
   }
   memset((char*)h + off_c, 0, 16);
-  TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, off_c + 16, cudaMemcpyHostToDevice, s));
+  rc = tadev_stage_upload(ctx, s, d, h, off_c + 16, uploaded);
+  if (rc) return rc;
   ctx->launches++;
   const tadev_gemm_group* dg = (const tadev_gemm_group*)d;
   const WsTask* dt = (const WsTask*)((char*)d + off_t);

@@ -284,7 +284,10 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
   }
   for (int b = 0; b < nb; ++b) {
     const int L = (int)my_rows.size();
-    const int lo = (int)((int64_t)L * b / nb), hi = (int)((int64_t)L * (b + 1) / nb);
+    // host-resident result: the download of the LAST block is not hidden by any GEMM, so that block gets
+    // half the rows of the others (weights 2,...,2,1)
+    const int64_t wtot = c_host && nb >= 2 ? 2 * (int64_t)nb - 1 : nb, wsc = c_host && nb >= 2 ? 2 : 1;
+    const int lo = (int)((int64_t)L * std::min<int64_t>(wsc * b, wtot) / wtot), hi = (int)((int64_t)L * std::min<int64_t>(wsc * (b + 1), wtot) / wtot);
     brange[b] = {lo, hi};
     const int row_lo = lo < L ? my_rows[lo] : Mt, row_hi = hi < L ? my_rows[hi] : Mt;  // global row bounds
     for (size_t si = 0; si < S.steps.size(); ++si) {
