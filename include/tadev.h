@@ -368,6 +368,21 @@ int tadev_contraction_eval(tadev_contraction* c, void* result_arena, int result_
                            tadev_contract_stats* stats);
 int tadev_contraction_destroy(tadev_contraction* c);
 
+/* ---- the element-wise engine -----------------------------------------------
+ * c(target) = alpha * a(a_idx) [ + beta * b(b_idx)   (TADEV_EW_AXPBY; b == NULL: scale / copy / permute)
+ *                              | .* b(b_idx)          (TADEV_EW_MULT: Hadamard product) ]
+ * replaces AddEngine / SubtEngine / ScalEngine / Hadamard MultEngine (expressions/add_engine.h,
+ * subt_engine.h, scal_engine.h, mult_engine.h). Result shape = SparseShape::scale / add / mult
+ * (sparse_shape.h:1243-1563). Same create / info / eval / destroy protocol as the contraction
+ * engine (the info struct is shared; grid and op fields are unused). Device-resident arrays. */
+typedef struct tadev_elementwise tadev_elementwise;
+int tadev_elementwise_create(tadev_ctx* ctx, int op, const char* target, double alpha, const char* a_idx,
+                             const tadev_array_desc* a, double beta, const char* b_idx /* or NULL */,
+                             const tadev_array_desc* b /* or NULL */, float threshold, tadev_elementwise** out);
+int tadev_elementwise_info_get(const tadev_elementwise* e, tadev_contraction_info* info);
+int tadev_elementwise_eval(tadev_elementwise* e, void* result_arena, float* ms /* device time, may be NULL */);
+int tadev_elementwise_destroy(tadev_elementwise* e);
+
 /* [host] the schedule the driver will execute, for inspection/tests: per step the root grid
  * column/row and the pair list of this rank. Arrays are caller-allocated with capacities.
  * pairs are (i,j) global tile coordinates in row-major order. */

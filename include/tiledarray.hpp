@@ -303,24 +303,77 @@ template <typename Tile, typename Policy> class DistArray;
 template <typename A> struct MultExpr;
 template <typename A> struct ScalMultExpr;
 
+template <typename A> struct ScalTsrExpr;
+template <typename A> struct AddExpr;
+
+namespace detail {
+inline std::vector<std::string> split_indices(const std::string& s) {
+  std::vector<std::string> out;
+  std::string cur;
+  for (char ch : s) {
+    if (ch == ',') { out.push_back(cur); cur.clear(); }
+    else if (ch != ' ' && ch != '\t') cur.push_back(ch);
+  }
+  if (!cur.empty() || !out.empty()) out.push_back(cur);
+  return out;
+}
+inline bool same_index_set(const std::string& a, const std::string& b) {
+  auto x = split_indices(a), y = split_indices(b);
+  std::sort(x.begin(), x.end());
+  std::sort(y.begin(), y.end());
+  return x == y;
+}
+}  // namespace detail
+
 template <typename A>
 struct TsrExpr {
   A* array;
   std::string idx;
   MultExpr<A> operator*(const TsrExpr& o) const { return MultExpr<A>{*this, o}; }
-  void operator=(const MultExpr<A>& e) { array->assign_contraction(idx, e.left, e.right, 1.0, false); }
-  void operator=(const ScalMultExpr<A>& e) { array->assign_contraction(idx, e.expr.left, e.expr.right, e.factor, false); }
-  void operator+=(const MultExpr<A>& e) { array->assign_contraction(idx, e.left, e.right, 1.0, true); }
-  void operator+=(const ScalMultExpr<A>& e) { array->assign_contraction(idx, e.expr.left, e.expr.right, e.factor, true); }
+  // products: a contraction, or — when every index is shared and kept — the Hadamard product (mult_engine.h)
+  void operator=(const MultExpr<A>& e) { assign_product(e.left, e.right, 1.0, false); }
+  void operator=(const ScalMultExpr<A>& e) { assign_product(e.expr.left, e.expr.right, e.factor, false); }
+  void operator+=(const MultExpr<A>& e) { assign_product(e.left, e.right, 1.0, true); }
+  void operator+=(const ScalMultExpr<A>& e) { assign_product(e.expr.left, e.expr.right, e.factor, true); }
+  // sums, scaling, copy / permutation (add_engine.h, subt_engine.h, scal_engine.h)
+  void operator=(const AddExpr<A>& e) { array->assign_elementwise(idx, TADEV_EW_AXPBY, e.l.f, e.l.t, e.r.f, &e.r.t); }
+  void operator=(const ScalTsrExpr<A>& e) { array->assign_elementwise(idx, TADEV_EW_AXPBY, e.f, e.t, 0.0, nullptr); }
+  void operator=(const TsrExpr& e) { array->assign_elementwise(idx, TADEV_EW_AXPBY, 1.0, e, 0.0, nullptr); }
+
+ private:
+  void assign_product(const TsrExpr& l, const TsrExpr& r, double factor, bool accumulate) {
+    if (detail::same_index_set(l.idx, r.idx) && detail::same_index_set(l.idx, idx)) {
+      TA_TADEV_ASSERT(!accumulate, "+= of a Hadamard product is not implemented");
+      array->assign_elementwise(idx, TADEV_EW_MULT, factor, l, 1.0, &r);
+    } else array->assign_contraction(idx, l, r, factor, accumulate);
+  }
 };
 template <typename A>
 struct MultExpr { TsrExpr<A> left, right; };
 template <typename A>
 struct ScalMultExpr { MultExpr<A> expr; double factor; };
+template <typename A>
+struct ScalTsrExpr { TsrExpr<A> t; double f; };
+template <typename A>
+struct AddExpr { ScalTsrExpr<A> l, r; };
 template <typename A> ScalMultExpr<A> operator*(double f, const MultExpr<A>& e) { return {e, f}; }
 template <typename A> ScalMultExpr<A> operator*(const MultExpr<A>& e, double f) { return {e, f}; }
 template <typename A> ScalMultExpr<A> operator*(double f, const ScalMultExpr<A>& e) { return {e.expr, f * e.factor}; }
 template <typename A> ScalMultExpr<A> operator-(const MultExpr<A>& e) { return {e, -1.0}; }
+template <typename A> ScalTsrExpr<A> operator*(double f, const TsrExpr<A>& t) { return {t, f}; }
+template <typename A> ScalTsrExpr<A> operator*(const TsrExpr<A>& t, double f) { return {t, f}; }
+template <typename A> ScalTsrExpr<A> operator*(double f, const ScalTsrExpr<A>& t) { return {t.t, f * t.f}; }
+template <typename A> ScalTsrExpr<A> operator-(const TsrExpr<A>& t) { return {t, -1.0}; }
+template <typename A> AddExpr<A> operator+(const TsrExpr<A>& l, const TsrExpr<A>& r) { return {{l, 1.0}, {r, 1.0}}; }
+template <typename A> AddExpr<A> operator-(const TsrExpr<A>& l, const TsrExpr<A>& r) { return {{l, 1.0}, {r, -1.0}}; }
+template <typename A> AddExpr<A> operator+(const ScalTsrExpr<A>& l, const TsrExpr<A>& r) { return {l, {r, 1.0}}; }
+template <typename A> AddExpr<A> operator-(const ScalTsrExpr<A>& l, const TsrExpr<A>& r) { return {l, {r, -1.0}}; }
+template <typename A> AddExpr<A> operator+(const TsrExpr<A>& l, const ScalTsrExpr<A>& r) { return {{l, 1.0}, r}; }
+template <typename A> AddExpr<A> operator-(const TsrExpr<A>& l, const ScalTsrExpr<A>& r) { return {{l, 1.0}, {r.t, -r.f}}; }
+template <typename A> AddExpr<A> operator+(const ScalTsrExpr<A>& l, const ScalTsrExpr<A>& r) { return {l, r}; }
+template <typename A> AddExpr<A> operator-(const ScalTsrExpr<A>& l, const ScalTsrExpr<A>& r) { return {l, {r.t, -r.f}}; }
+template <typename A> AddExpr<A> operator*(double f, const AddExpr<A>& e) { return {{e.l.t, f * e.l.f}, {e.r.t, f * e.r.f}}; }
+template <typename A> AddExpr<A> operator-(const AddExpr<A>& e) { return {{e.l.t, -e.l.f}, {e.r.t, -e.r.f}}; }
 
 // knobs of the evaluator (TA_SUMMA_* analogues); see tadev_contract_options
 struct ContractionOptions {
@@ -436,6 +489,63 @@ class DistArray {
   }
   TsrExpr<DistArray> operator()(const std::string& idx) { return {this, idx}; }
 
+  // c(target) = alpha * a(idx_a) [+ beta * b(idx_b) | .* b(idx_b)] — the element-wise engines
+  void assign_elementwise(const std::string& target, int op, double alpha, const TsrExpr<DistArray>& a, double beta,
+                          const TsrExpr<DistArray>* b) {
+    DistArray& A = *a.array;
+    TA_TADEV_ASSERT(A.st_ && (!b || b->array->st_), "element-wise expression: uninitialized argument");
+    World& w = A.world();
+    A.allocate_();
+    if (b) b->array->allocate_();
+    Desc da(A);
+    std::unique_ptr<Desc> db(b ? new Desc(*b->array) : nullptr);
+    tadev_elementwise* eng = nullptr;
+    check(tadev_elementwise_create(w.ctx(), op, target.c_str(), alpha, a.idx.c_str(), &da.d, beta, b ? b->idx.c_str() : nullptr,
+                                   b ? &db->d : nullptr, shape_type::threshold(), &eng));
+    std::shared_ptr<tadev_elementwise> guard(eng, [](tadev_elementwise* e) { tadev_elementwise_destroy(e); });
+    tadev_contraction_info info;
+    check(tadev_elementwise_info_get(eng, &info));
+    auto ns = adopt_structure_(w, info, Device);
+    check(tadev_elementwise_eval(eng, ns->arena, nullptr));
+    if (w.size() > 1) ns->owner = A.st_->owner;  // operands are in the target's order: same process map
+    st_ = ns;  // the old tiles (possibly operands) are freed stream-ordered after the kernel
+  }
+
+  // Frobenius norms of the local tiles over the tile grid (zeros elsewhere), computed on the device
+  Tensor<float> tile_norms() const {
+    const State& s = *st_;
+    TA_TADEV_ASSERT(s.mem == Device, "tile_norms: device-resident arrays only");
+    Tensor<float> out(Range(s.trange.tiles_extent()), 0.0f);
+    std::vector<const double*> ptrs;
+    std::vector<int64_t> sizes, ords;
+    for (int64_t o = 0; o < size(); ++o) if (!s.tiles.empty() && s.tiles[o]) { ptrs.push_back((const double*)s.tiles[o]); sizes.push_back(s.elems[o]); ords.push_back(o); }
+    if (ptrs.empty()) return out;
+    tadev_ctx* ctx = world().ctx();
+    tadev_stream st = world().stream();
+    void *d_p = nullptr, *d_s = nullptr, *d_o = nullptr;
+    const size_t n = ptrs.size();
+    check(tadev_alloc(ctx, n * 8, &d_p, st)); check(tadev_alloc(ctx, n * 8, &d_s, st)); check(tadev_alloc(ctx, n * 8, &d_o, st));
+    check(tadev_memcpy_h2d(ctx, d_p, ptrs.data(), n * 8, st));
+    check(tadev_memcpy_h2d(ctx, d_s, sizes.data(), n * 8, st));
+    check(tadev_tile_sqnorms_f64(ctx, st, (int)n, (const double* const*)d_p, (const int64_t*)d_s, (double*)d_o));
+    std::vector<double> sq(n);
+    check(tadev_memcpy_d2h(ctx, sq.data(), d_o, n * 8, st));
+    check(tadev_stream_sync(ctx, st));
+    tadev_free(ctx, d_p, st); tadev_free(ctx, d_s, st); tadev_free(ctx, d_o, st);
+    for (size_t t = 0; t < n; ++t) out[(size_t)ords[t]] = (float)std::sqrt(sq[t]);
+    return out;
+  }
+  // truncate (dist_array.h:1553, conversions/truncate.h): rebuild the shape from the true tile norms and drop
+  // the tiles that fall below the threshold. Dense arrays are unchanged. (Single-rank worlds: a multi-rank
+  // world needs the max-reduction of the norms over ranks, sparse_shape.h:416.)
+  void truncate() {
+    if (!is_sparse) return;
+    TA_TADEV_ASSERT(world().size() == 1, "truncate: multi-rank worlds are not supported by the C++ layer yet");
+    shape_type ns(world(), tile_norms(), st_->trange);
+    for (int64_t o = 0; o < size(); ++o) if (ns.is_zero(o) && !st_->tiles.empty()) { st_->tiles[o] = nullptr; st_->elems[o] = 0; }
+    st_->shape = ns;
+  }
+
   // c(target) (+)= factor * left * right — ExprEngine hand-off (expr.h:378 eval_to)
   void assign_contraction(const std::string& target, const TsrExpr<DistArray>& l, const TsrExpr<DistArray>& r, double factor, bool accumulate) {
     DistArray &A = *l.array, &B = *r.array;
@@ -448,10 +558,7 @@ class DistArray {
     std::shared_ptr<tadev_contraction> guard(eng, [](tadev_contraction* e) { tadev_contraction_destroy(e); });
     tadev_contraction_info info;
     check(tadev_contraction_info_get(eng, &info));
-    std::vector<TiledRange1> dims;
-    size_t off = 0;
-    for (int d = 0; d < info.rank; ++d) { dims.emplace_back(info.bounds + off, info.bounds + off + info.ntiles[d] + 1); off += (size_t)info.ntiles[d] + 1; }
-    TiledRange tr(dims.begin(), dims.end());
+    const TiledRange tr = trange_of_(info);
     const Memory mem = st_ ? st_->mem : Device;
     TA_TADEV_ASSERT(mem != Lazy, "the result of a contraction cannot be a lazy array");
     std::shared_ptr<State> ns;
@@ -461,21 +568,8 @@ class DistArray {
       ns = st_;
     } else {
       TA_TADEV_ASSERT(!st_ || st_->trange.rank() == 0 || st_->trange == tr || st_->tiles.empty(), "result array tiling does not match the expression");
-      ns = std::make_shared<State>();
-      ns->world = &w; ns->trange = tr; ns->mem = mem;
       if (this != &A && this != &B) st_.reset();  // give the old result back to the pool before allocating the new one
-      ns->alloc_arena(info.arena_elems);
-      ns->tiles.assign((size_t)tr.ntiles(), nullptr);
-      ns->elems.assign((size_t)tr.ntiles(), 0);
-      for (int64_t t = 0; t < info.nlocal; ++t) {
-        ns->tiles[info.ordinals[t]] = (char*)ns->arena + info.offsets[t] * 8;
-        ns->elems[info.ordinals[t]] = info.elems[t];
-      }
-      if (info.norms) {
-        Tensor<float> nt(Range(tr.tiles_extent()));
-        std::memcpy(nt.data(), info.norms, nt.size() * 4);
-        ns->shape = shape_type::from_scaled(std::move(nt), (int64_t)info.nzero);
-      }
+      ns = adopt_structure_(w, info, mem);
       ns->owner = [guard](int64_t ord) { int o = 0; check(tadev_contraction_owner(guard.get(), ord, &o)); return o; };
     }
     check(tadev_contraction_eval(eng, ns->arena, mem, accumulate ? 1 : 0, &ContractionOptions::last_stats()));
@@ -505,6 +599,30 @@ class DistArray {
       else tadev_free(world->ctx(), arena, world->stream());
     }
   };
+  static TiledRange trange_of_(const tadev_contraction_info& info) {
+    std::vector<TiledRange1> dims;
+    size_t off = 0;
+    for (int d = 0; d < info.rank; ++d) { dims.emplace_back(info.bounds + off, info.bounds + off + info.ntiles[d] + 1); off += (size_t)info.ntiles[d] + 1; }
+    return TiledRange(dims.begin(), dims.end());
+  }
+  // a fresh State with the tiling, shape, arena and tile table an engine's info struct describes
+  static std::shared_ptr<State> adopt_structure_(World& w, const tadev_contraction_info& info, Memory mem) {
+    auto ns = std::make_shared<State>();
+    ns->world = &w; ns->trange = trange_of_(info); ns->mem = mem;
+    ns->alloc_arena(info.arena_elems);
+    ns->tiles.assign((size_t)ns->trange.ntiles(), nullptr);
+    ns->elems.assign((size_t)ns->trange.ntiles(), 0);
+    for (int64_t t = 0; t < info.nlocal; ++t) {
+      ns->tiles[info.ordinals[t]] = (char*)ns->arena + info.offsets[t] * 8;
+      ns->elems[info.ordinals[t]] = info.elems[t];
+    }
+    if (info.norms) {
+      Tensor<float> nt(Range(ns->trange.tiles_extent()));
+      std::memcpy(nt.data(), info.norms, nt.size() * 4);
+      ns->shape = shape_type::from_scaled(std::move(nt), (int64_t)info.nzero);
+    }
+    return ns;
+  }
   struct Desc {  // tadev_array_desc of an array plus the storage it points to
     tadev_array_desc d{};
     std::vector<int64_t> bounds;

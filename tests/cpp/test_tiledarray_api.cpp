@@ -202,6 +202,71 @@ int main(int argc, char** argv) {
     CHECK(TA::ContractionOptions::last_stats().summa.lazy_tiles == 0);
   }
 
+  {  // element-wise expressions (tests/expressions_impl.h add / subt / scale / mult / permute blocks) + truncate
+    const TiledRange1 d1{0, 3, 10, 16}, d2{0, 5, 8, 21};
+    TA::TArrayD a(world, TiledRange{d1, d2}), b(world, TiledRange{d1, d2}), bt(world, TiledRange{d2, d1}), c, ct;
+    std::vector<double> A, B, BT;
+    fill_ints(a, &A); fill_ints(b, &B); fill_ints(bt, &BT);
+    const int R = 16, Cn = 21;
+    auto check_all = [&](const TA::TArrayD& arr, auto&& f) {
+      const auto X = to_host(arr);
+      bool ok = X.size() == (size_t)R * Cn;
+      for (int i = 0; i < R && ok; ++i) for (int j = 0; j < Cn; ++j) ok = ok && X[(size_t)i * Cn + j] == f(i, j);
+      return ok;
+    };
+    c("i,j") = a("i,j") + b("i,j");
+    CHECK(check_all(c, [&](int i, int j) { return A[i * Cn + j] + B[i * Cn + j]; }));
+    c("i,j") = a("i,j") - b("i,j");
+    CHECK(check_all(c, [&](int i, int j) { return A[i * Cn + j] - B[i * Cn + j]; }));
+    c("i,j") = 2.0 * a("i,j") + 3.0 * bt("j,i");
+    CHECK(check_all(c, [&](int i, int j) { return 2 * A[i * Cn + j] + 3 * BT[j * R + i]; }));
+    c("i,j") = -(a("i,j") - 2.0 * b("i,j"));
+    CHECK(check_all(c, [&](int i, int j) { return -(A[i * Cn + j] - 2 * B[i * Cn + j]); }));
+    c("i,j") = a("i,j") * b("i,j");  // Hadamard
+    CHECK(check_all(c, [&](int i, int j) { return A[i * Cn + j] * B[i * Cn + j]; }));
+    c("i,j") = 0.5 * (a("i,j") * bt("j,i"));
+    CHECK(check_all(c, [&](int i, int j) { return 0.5 * A[i * Cn + j] * BT[j * R + i]; }));
+    c("i,j") = 4.0 * a("i,j");
+    CHECK(check_all(c, [&](int i, int j) { return 4 * A[i * Cn + j]; }));
+    c("i,j") = c("i,j") + a("i,j");  // the result is also an operand
+    CHECK(check_all(c, [&](int i, int j) { return 5 * A[i * Cn + j]; }));
+    ct("j,i") = a("i,j");  // pure permutation
+    const auto CT = to_host(ct);
+    bool ok = true;
+    for (int i = 0; i < R; ++i) for (int j = 0; j < Cn; ++j) ok = ok && CT[(size_t)j * R + i] == A[i * Cn + j];
+    CHECK(ok);
+
+    // sparse: a - a keeps a's tiles in the estimated shape; truncate() finds them all zero
+    const TiledRange1 d = TiledRange1::make_uniform(32, 8);
+    const TiledRange tr{d, d};
+    TA::Tensor<float> norms(tadev::Range{4, 4}, 0.0f);
+    std::vector<Tensor> tiles;
+    lcg_state = 4242u;
+    for (int64_t o = 0; o < 16; ++o) {
+      Tensor t(tr.tile_extent(o));
+      const bool keep = (o % 3) != 1;
+      for (size_t i = 0; i < t.size(); ++i) t[i] = keep ? small_int() + 5.0 : 0.0;
+      norms[(size_t)o] = (float)t.norm();
+      tiles.push_back(t);
+    }
+    TA::TSpArrayD sa(world, tr, TA::SparseShape<float>(world, norms, tr)), sc;
+    for (int64_t o = 0; o < 16; ++o) if (!sa.is_zero(o)) sa.set(o, tiles[(size_t)o]);
+    sc("i,j") = sa("i,j") - sa("i,j");
+    CHECK(sc.shape().zero_tile_count() == sa.shape().zero_tile_count());
+    bool allzero = true;
+    for (double v : to_host(sc)) allzero = allzero && v == 0.0;
+    CHECK(allzero);
+    sc.truncate();
+    CHECK(sc.shape().zero_tile_count() == 16);
+    sc("i,j") = 2.0 * sa("i,j");
+    sc.truncate();  // true norms of 2a == 2 * norms of a: same zero pattern
+    for (int64_t o = 0; o < 16; ++o) CHECK(sc.is_zero(o) == sa.is_zero(o));
+    const auto S2 = to_host(sc), S1 = to_host(sa);
+    ok = true;
+    for (size_t i = 0; i < S1.size(); ++i) ok = ok && S2[i] == 2 * S1[i];
+    CHECK(ok);
+  }
+
   TA::finalize();
   if (failures == 0) std::printf("ALL TILEDARRAY API TESTS PASSED\n");
   return failures == 0 ? 0 : 1;

@@ -150,6 +150,11 @@ PROTOTYPES = {
     "tadev_contraction_owner": (_i, [_vp, _i64, _P(_i)]),
     "tadev_contraction_eval": (_i, [_vp, _vp, _i, _i, _P(ContractStatsC)]),
     "tadev_contraction_destroy": (_i, [_vp]),
+    "tadev_elementwise_create": (_i, [_vp, _i, C.c_char_p, _d, C.c_char_p, _P(ArrayDescC), _d, C.c_char_p, _P(ArrayDescC), _f,
+                                      _P(_vp)]),
+    "tadev_elementwise_info_get": (_i, [_vp, _P(ContractionInfoC)]),
+    "tadev_elementwise_eval": (_i, [_vp, _vp, _P(_f)]),
+    "tadev_elementwise_destroy": (_i, [_vp]),
     "tadev_comm_unique_id": (_i, [_vp]),
     "tadev_comm_init": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "tadev_comm_destroy": (_i, [_vp]),

@@ -552,3 +552,248 @@ extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, 
   if (stats) { stats->summa = st; stats->permute_ms = permute_ms; }
   return TADEV_OK;
 }
+
+// =================================================================================================
+// Element-wise engine: c(idx) = alpha * a(idx_a) [ + beta * b(idx_b) | .* b(idx_b) ]
+// The reference's AddEngine / SubtEngine / ScalEngine / Hadamard MultEngine (expressions/add_engine.h,
+// subt_engine.h, scal_engine.h, mult_engine.h) for arrays described through the C ABI. Operands whose
+// index order differs from the target are permuted first (one batched launch per tile extent), then
+// ONE tadev_tiles_binary_f64 launch produces every result tile. Result shapes follow
+// SparseShape::scale / add / mult (sparse_shape.h:1243-1262, 1309-1331, 1522-1563) in fp32, operation
+// by operation.
+namespace {
+
+std::vector<std::string> split_idx(const char* s) {
+  std::vector<std::string> out;
+  std::string cur;
+  for (const char* p = s; *p; ++p) {
+    if (*p == ',') { out.push_back(cur); cur.clear(); }
+    else if (*p != ' ' && *p != '\t') cur.push_back(*p);
+  }
+  if (!cur.empty() || !out.empty()) out.push_back(cur);
+  return out;
+}
+
+// hard-zero below the threshold, count zeros (screen step shared by scale / add / mult)
+uint64_t screen(std::vector<float>& v, float thr) {
+  uint64_t nz = 0;
+  for (float& x : v) if (x < thr) { x = 0.0f; ++nz; }
+  return nz;
+}
+
+}  // namespace
+
+struct tadev_elementwise {
+  tadev_ctx* ctx = nullptr;
+  int op = 0;
+  double alpha = 1.0, beta = 0.0;
+  float thr = 0.0f;
+  bool has_b = false;
+  Operand A, B;
+  TRange tr;                       // result tiling (target order)
+  bool sparse = false;
+  std::vector<float> norms;        // result shape
+  uint64_t nzero = 0;
+  std::vector<int64_t> ords, elems, offs;
+  int64_t arena_elems = 2;
+  std::vector<int64_t> tb_flat;
+  std::vector<int32_t> tn;
+};
+
+static int ew_prepare_operand(Operand& o, const std::vector<std::string>& idx, const std::vector<std::string>& target, const char* who) {
+  TADEV_REQUIRE((int)idx.size() == o.tr.rank(), "%s: index list rank does not match the array", who);
+  TADEV_REQUIRE(idx.size() == target.size(), "%s: indices do not match the target", who);
+  TADEV_REQUIRE(o.d.memory == TADEV_MEM_DEVICE, "%s: element-wise expressions take device-resident arrays", who);
+  int32_t perm[16];
+  bool ident = true;
+  for (size_t i = 0; i < idx.size(); ++i) {
+    const size_t p = std::find(target.begin(), target.end(), idx[i]) - target.begin();
+    TADEV_REQUIRE(p < target.size(), "%s: index '%s' is not in the target", who, idx[i].c_str());
+    for (size_t j = 0; j < i; ++j) TADEV_REQUIRE(idx[j] != idx[i], "%s: repeated index '%s'", who, idx[i].c_str());
+    perm[i] = (int32_t)p;
+    ident = ident && p == i;
+  }
+  if (ident) perm[0] = -1;
+  return build_operand_structure(o, perm, (int)idx.size());
+}
+
+extern "C" int tadev_elementwise_create(tadev_ctx* ctx, int op, const char* target, double alpha, const char* a_idx,
+                                        const tadev_array_desc* a, double beta, const char* b_idx, const tadev_array_desc* b,
+                                        float threshold, tadev_elementwise** out) {
+  TADEV_REQUIRE(ctx && target && a_idx && a && out, "tadev_elementwise_create: null");
+  TADEV_REQUIRE(op == TADEV_EW_AXPBY || op == TADEV_EW_MULT, "tadev_elementwise_create: bad op %d", op);
+  TADEV_REQUIRE((b == nullptr) == (b_idx == nullptr), "tadev_elementwise_create: b and b_idx go together");
+  TADEV_REQUIRE(b || op == TADEV_EW_AXPBY, "tadev_elementwise_create: a Hadamard product needs two operands");
+  std::unique_ptr<tadev_elementwise> E(new tadev_elementwise());
+  E->ctx = ctx; E->op = op; E->alpha = alpha; E->beta = b ? beta : 0.0; E->thr = threshold; E->has_b = b != nullptr;
+  const auto T = split_idx(target);
+  int rc = copy_operand(a, E->A, "tadev_elementwise_create(a)");
+  if (!rc) rc = ew_prepare_operand(E->A, split_idx(a_idx), T, "tadev_elementwise_create(a)");
+  if (!rc && b) rc = copy_operand(b, E->B, "tadev_elementwise_create(b)");
+  if (!rc && b) rc = ew_prepare_operand(E->B, split_idx(b_idx), T, "tadev_elementwise_create(b)");
+  if (rc) return rc;
+  TADEV_REQUIRE(ctx->nranks == 1 || (E->A.perm.empty() && (!b || E->B.perm.empty())),
+                "multi-rank element-wise expressions need operands in the target's index order (no redistribution)");
+  E->tr = E->A.ptr;
+  if (b) {
+    TADEV_REQUIRE(E->B.ptr.b == E->tr.b, "element-wise expression: operand tilings differ");
+    TADEV_REQUIRE(E->A.dense() == E->B.dense(), "mixed dense/sparse element-wise expression is not supported");
+  }
+  E->sparse = !E->A.dense();
+  const int64_t n = E->tr.total();
+  if (E->sparse) {
+    const float fa = (float)std::fabs(alpha), fb = (float)std::fabs(beta);
+    std::vector<float> r = E->A.pnorms;
+    if (!b) { for (float& x : r) x *= fa; E->nzero = screen(r, threshold); }
+    else if (op == TADEV_EW_AXPBY) {
+      std::vector<float> sb = E->B.pnorms;
+      for (float& x : r) x *= fa;
+      screen(r, threshold);                              // leaf scaling, each thresholded (ScalTsrExpr shapes)
+      for (float& x : sb) x *= fb;
+      screen(sb, threshold);
+      for (int64_t i = 0; i < n; ++i) r[i] = r[i] + sb[i];
+      E->nzero = screen(r, threshold);
+    } else {
+      for (int64_t i = 0; i < n; ++i) r[i] = r[i] * E->B.pnorms[i];
+      if (alpha != 1.0) for (float& x : r) x *= fa;
+      // scale_tile_norms<ScaleBy::Volume>: rank 1 norm *= size, else norm *= (x * y) of the two outer products
+      const int R = E->tr.rank();
+      if (R == 1) { for (int64_t i = 0; i < n; ++i) r[i] *= (float)E->tr.ext(0, i); }
+      else {
+        const int middle = (R >> 1) + (R & 1);
+        const std::vector<float> l = recursive_outer(E->tr, 0, middle), rr = recursive_outer(E->tr, middle, R);
+        for (size_t i = 0; i < l.size(); ++i)
+          for (size_t j = 0; j < rr.size(); ++j) { const float xy = l[i] * rr[j]; r[i * rr.size() + j] *= xy; }
+      }
+      E->nzero = screen(r, threshold);
+    }
+    E->norms.swap(r);
+  }
+  // local result tiles: non-zero in the result shape and (multi-rank) held by this rank in an operand
+  const std::vector<int64_t> tshape = E->tr.tiles_shape();
+  std::vector<int64_t> idx;
+  int64_t off = 0;
+  for (int64_t o = 0; o < n; ++o) {
+    if (E->sparse && E->norms[o] < threshold) continue;
+    if (ctx->nranks > 1 && !(E->A.tiles[o] || (b && E->B.tiles[o]))) continue;
+    unravel(o, tshape, idx);
+    int64_t e = 1;
+    for (int d = 0; d < E->tr.rank(); ++d) e *= E->tr.ext(d, idx[d]);
+    E->ords.push_back(o); E->elems.push_back(e); E->offs.push_back(off);
+    off += (e + 1) & ~(int64_t)1;
+  }
+  E->arena_elems = std::max<int64_t>(off, 2);
+  for (int d = 0; d < E->tr.rank(); ++d) {
+    E->tn.push_back((int32_t)E->tr.ntiles(d));
+    E->tb_flat.insert(E->tb_flat.end(), E->tr.b[d].begin(), E->tr.b[d].end());
+  }
+  *out = E.release();
+  return TADEV_OK;
+}
+
+extern "C" int tadev_elementwise_info_get(const tadev_elementwise* E, tadev_contraction_info* info) {
+  TADEV_REQUIRE(E && info, "tadev_elementwise_info_get: null");
+  memset(info, 0, sizeof(*info));
+  info->rank = E->tr.rank();
+  info->bounds = E->tb_flat.data();
+  info->ntiles = E->tn.data();
+  info->norms = E->sparse ? E->norms.data() : nullptr;
+  info->nzero = E->nzero;
+  info->nlocal = (int64_t)E->ords.size();
+  info->ordinals = E->ords.data();
+  info->elems = E->elems.data();
+  info->offsets = E->offs.data();
+  info->arena_elems = E->arena_elems;
+  info->Pr = E->ctx->Pr; info->Pc = E->ctx->Pc;
+  return TADEV_OK;
+}
+
+namespace {
+
+// device pointers of the operand's tiles by TARGET ordinal (nullptr = zero tile); operands in another
+// index order are permuted into a temporary arena first
+int ew_operand_tiles(tadev_ctx* ctx, Operand& o, std::vector<const double*>& by_target, double** tmp_arena) {
+  const int64_t n = o.tr.total();
+  by_target.assign((size_t)n, nullptr);
+  *tmp_arena = nullptr;
+  if (o.perm.empty()) {
+    for (int64_t t = 0; t < n; ++t) by_target[t] = static_cast<const double*>(o.tiles[t]);
+    return TADEV_OK;
+  }
+  const int R = o.tr.rank();
+  const std::vector<int64_t> tshape = o.tr.tiles_shape(), pshape = o.ptr.tiles_shape();
+  std::vector<int64_t> idx, pidx(R), ords, exts, offs;
+  int64_t off = 0;
+  for (int64_t t = 0; t < n; ++t) {
+    if (!o.tiles[t]) continue;
+    ords.push_back(t);
+    unravel(t, tshape, idx);
+    int64_t vol = 1;
+    for (int d = 0; d < R; ++d) { exts.push_back(o.tr.ext(d, idx[d])); vol *= exts.back(); }
+    offs.push_back(off);
+    off += (vol + 1) & ~(int64_t)1;
+  }
+  tadev_stream s = (tadev_stream)ctx->streams[0];
+  int rc = tadev_alloc(ctx, (size_t)std::max<int64_t>(off, 2) * 8, (void**)tmp_arena, s);
+  if (rc) return rc;
+  std::vector<char> done(ords.size(), 0);
+  std::vector<const void*> ins;
+  std::vector<void*> outs;
+  std::vector<int32_t> perm32(o.perm.begin(), o.perm.end());
+  for (size_t t = 0; t < ords.size(); ++t) {
+    unravel(ords[t], tshape, idx);
+    for (int i = 0; i < R; ++i) pidx[o.perm[i]] = idx[i];
+    by_target[ravel(pidx, pshape)] = *tmp_arena + offs[t];
+    if (done[t]) continue;
+    ins.clear(); outs.clear();
+    for (size_t q = t; q < ords.size(); ++q) {
+      if (done[q] || memcmp(&exts[q * R], &exts[t * R], sizeof(int64_t) * R) != 0) continue;
+      ins.push_back(o.tiles[ords[q]]);
+      outs.push_back(*tmp_arena + offs[q]);
+      done[q] = 1;
+    }
+    rc = tadev_permute_batched(ctx, s, R, &exts[t * R], perm32.data(), 8, (int)ins.size(), ins.data(), outs.data());
+    if (rc) return rc;
+  }
+  return TADEV_OK;
+}
+
+}  // namespace
+
+extern "C" int tadev_elementwise_eval(tadev_elementwise* E, void* result_arena, float* ms_out) {
+  TADEV_REQUIRE(E && result_arena, "tadev_elementwise_eval: null");
+  tadev_ctx* ctx = E->ctx;
+  tadev_stream s = (tadev_stream)ctx->streams[0];
+  void *e0 = nullptr, *e1 = nullptr;
+  tadev_event_create(ctx, &e0); tadev_event_create(ctx, &e1);
+  tadev_event_record(ctx, e0, s);
+  std::vector<const double*> ta, tb;
+  double *tmpA = nullptr, *tmpB = nullptr;
+  int rc = ew_operand_tiles(ctx, E->A, ta, &tmpA);
+  if (!rc && E->has_b) rc = ew_operand_tiles(ctx, E->B, tb, &tmpB);
+  if (!rc && !E->ords.empty()) {
+    const size_t n = E->ords.size();
+    std::vector<double*> out(n);
+    std::vector<const double*> x(n), y(n, nullptr);
+    double* arena = static_cast<double*>(result_arena);
+    for (size_t t = 0; t < n; ++t) {
+      out[t] = arena + E->offs[t];
+      x[t] = ta[E->ords[t]];
+      if (E->has_b) y[t] = tb[E->ords[t]];
+    }
+    rc = tadev_tiles_binary_f64(ctx, s, E->op, (int)n, out.data(), x.data(), y.data(), E->elems.data(), E->alpha, E->beta);
+  }
+  if (tmpA) tadev_free(ctx, tmpA, s);
+  if (tmpB) tadev_free(ctx, tmpB, s);
+  tadev_event_record(ctx, e1, s);
+  float ms = 0;
+  tadev_event_elapsed_ms(ctx, e0, e1, &ms);
+  tadev_event_destroy(ctx, e0); tadev_event_destroy(ctx, e1);
+  if (ms_out) *ms_out = ms;
+  return rc;
+}
+
+extern "C" int tadev_elementwise_destroy(tadev_elementwise* E) {
+  delete E;
+  return TADEV_OK;
+}

@@ -610,9 +610,10 @@ class ContractionStats:
 class ElementwiseEngine:
     """c(idx) = alpha * a(idx_a) (+ beta * b(idx_b) | .* b(idx_b)): the reference's AddEngine / SubtEngine /
     ScalEngine / MultEngine-Hadamard (expressions/add_engine.h, subt_engine.h, scal_engine.h, mult_engine.h)
-    for device arrays. Operands whose index order differs from the target are permuted first (one batched
-    tadev_permute_batched launch per tile extent); then ONE tadev_tiles_binary_f64 launch produces every
-    result tile. Result shape: SparseShape::scale / add / mult."""
+    for device arrays. The engine is native (csrc/cont_engine.cpp behind tadev_elementwise_create/_eval):
+    operands whose index order differs from the target are permuted first (one batched launch per tile
+    extent); then ONE tadev_tiles_binary_f64 launch produces every result tile. Result shape:
+    SparseShape::scale / add / mult. This class only describes the arrays and adopts the result."""
 
     last_ms: float = 0.0
 
@@ -621,85 +622,55 @@ class ElementwiseEngine:
         self.world = a.array.world
         self.dev = self.world.dev
 
-    def _aligned(self, leaf: "TsrExpr"):
-        """(trange, shape, {ordinal: ptr}, temp arena or None) of the operand in TARGET index order."""
-        arr, tgt = leaf.array, self.result.indices
-        _ta_assert(arr.memory == "device", "element-wise expressions: device-resident arrays only")
-        _ta_assert(sorted(leaf.indices) == sorted(tgt), f"indices {leaf.indices} do not match the target {tgt}")
-        arr._allocate()
-        if leaf.indices == tgt:
-            return arr.trange, arr.shape, {o: b.ptr for o, b in arr.tiles.items()}, None
-        perm = [tgt.index(x) for x in leaf.indices]  # image form: result[perm[i]] = arg[i]
-        rank = len(perm)
-        dims = [None] * rank
-        for i, p in enumerate(perm):
-            dims[p] = arr.trange.dims[i]
-        tr = TiledRange(dims)
-        shape = arr.shape.perm(perm) if not arr.shape.is_dense() else arr.shape
-        ords = np.fromiter(arr.tiles.keys(), dtype=np.int64, count=len(arr.tiles))
-        ptrs = np.fromiter((b_.ptr for b_ in arr.tiles.values()), dtype=np.uint64, count=len(arr.tiles))
-        if not len(ords):
-            return tr, shape, {}, None
-        idx = np.stack(np.unravel_index(ords, arr.trange.tiles_shape), axis=1)
-        ext = np.stack([np.asarray(d.extents, dtype=np.int64)[idx[:, a_]] for a_, d in enumerate(arr.trange.dims)], axis=1)
-        pidx = np.empty_like(idx)
-        pidx[:, perm] = idx
-        pords = np.ravel_multi_index(tuple(pidx.T), tr.tiles_shape).astype(np.int64)
-        elems = ext.prod(axis=1)
-        offs = np.concatenate([[0], np.cumsum((elems + 1) & ~1)]).astype(np.int64)
-        arena = self.dev.alloc(max(int(offs[-1]), 2) * 8)
-        dst = (arena.ptr + offs[:-1] * 8).astype(np.uint64)
-        uniq, inv = np.unique(ext, axis=0, return_inverse=True)
-        inv = inv.ravel()
-        for u in range(len(uniq)):
-            sel = np.nonzero(inv == u)[0]
-            self.dev.permute_batched_ptrs(tuple(int(x) for x in uniq[u]), perm, 8, ptrs[sel], dst[sel])
-        return tr, shape, dict(zip(pords.tolist(), dst.tolist())), arena
-
     def eval(self) -> None:
-        dev, w = self.dev, self.world
+        dev, w, lib = self.dev, self.world, self.world.lib
         Cres = self.result.array
         _ta_assert(Cres.memory == "device", "element-wise expressions: device-resident result only")
-        with dev.timer() as tm:
-            trA, shA, tA, tmpA = self._aligned(self.a)
-            if self.b is not None:
-                trB, shB, tB, tmpB = self._aligned(self.b)
-                _ta_assert(trA == trB, "element-wise expression: operand tilings differ")
-                _ta_assert(shA.is_dense() == shB.is_dense(), "mixed dense/sparse element-wise expression is not supported")
+        keep: list = []
+        self.a.array._allocate()
+        dA = ContEngine._describe(self.a.array, keep)
+        dB = None
+        if self.b is not None:
+            self.b.array._allocate()
+            dB = ContEngine._describe(self.b.array, keep)
+        handle = C.c_void_p()
+        rc = lib.tadev_elementwise_create(dev.ctx, self.op, ",".join(self.result.indices).encode(), self.alpha,
+                                          ",".join(self.a.indices).encode(), C.byref(dA), self.beta,
+                                          ",".join(self.b.indices).encode() if self.b is not None else None,
+                                          C.byref(dB) if dB is not None else None, SparseShape._threshold, C.byref(handle))
+        if rc == _lib.EINVAL:
+            raise TiledArrayException(lib.tadev_last_error().decode())
+        check(rc)
+        try:
+            info = _lib.ContractionInfoC()
+            check(lib.tadev_elementwise_info_get(handle, C.byref(info)))
+            dims, off = [], 0
+            for d in range(info.rank):
+                n = info.ntiles[d]
+                dims.append(TiledRange1(*[info.bounds[off + t] for t in range(n + 1)]))
+                off += n + 1
+            tr = TiledRange(dims)
+            nloc = info.nlocal
+            ords = np.ctypeslib.as_array(info.ordinals, shape=(nloc,)).copy() if nloc else np.zeros(0, dtype=np.int64)
+            elems = np.ctypeslib.as_array(info.elems, shape=(nloc,)).copy() if nloc else np.zeros(0, dtype=np.int64)
+            offs = np.ctypeslib.as_array(info.offsets, shape=(nloc,)).copy() if nloc else np.zeros(0, dtype=np.int64)
+            if info.norms:
+                norms = np.ctypeslib.as_array(info.norms, shape=(max(tr.ntiles, 1),)).copy().reshape(tr.tiles_shape)
+                sv = [np.asarray(d.extents, dtype=f32) for d in tr.dims]
+                shape = SparseShape(w, None, None, _prebuilt=(norms, sv, int(info.nzero), SparseShape._threshold))
             else:
-                trB, shB, tB, tmpB = trA, shA, {}, None
-            # result shape (leaf scaling first, like ScalTsrExpr feeding Add/MultEngine)
-            if shA.is_dense():
                 shape = DenseShape()
-            elif self.b is None:
-                shape = shA.scale(self.alpha)
-            elif self.op == _lib.EW_MULT:
-                shape = shA.mult(shB, self.alpha)
-            else:
-                shape = shA.scale(self.alpha).add(shB.scale(self.beta))
-            r = w.rank
-            own = self.a.array._owner if self.a.indices == self.result.indices else (lambda o: 0)
-            _ta_assert(w.size == 1 or self.a.indices == self.result.indices,
-                       "multi-rank element-wise expressions need operands in the target's index order (no redistribution)")
-            ords = [o for o in range(trA.ntiles) if own(o) == r and not shape.is_zero(o)]
-            elems = np.asarray([int(np.prod(trA.tile_extent(trA.tile_index(o)), dtype=np.int64)) for o in ords], dtype=np.int64)
-            offs = np.concatenate([[0], np.cumsum((elems + 1) & ~1)]).astype(np.int64)
-            arena = dev.alloc(max(int(offs[-1]), 2) * 8)
-            out = (arena.ptr + offs[:-1] * 8).astype(np.uint64)
-            x = np.asarray([tA.get(o, 0) for o in ords], dtype=np.uint64)
-            y = np.asarray([tB.get(o, 0) for o in ords], dtype=np.uint64)
-            if len(ords):
-                dev.tiles_binary(self.op, out, x, y, elems, self.alpha, self.beta)
-            for t in (tmpA, tmpB):
-                if t is not None:
-                    t.free()
-        ElementwiseEngine.last_ms = tm.ms
-        if Cres is not self.a.array and (self.b is None or Cres is not self.b.array):
-            Cres.release()
-        else:  # c = c + b: the old tiles were operands; drop them now
-            Cres.release()
-        Cres.trange, Cres.shape, Cres._arena = trA, shape, arena
-        Cres.tiles = {o: DeviceBuffer(dev, int(p), int(e) * 8, False) for o, p, e in zip(ords, out.tolist(), elems.tolist())}
+            arena = dev.alloc(int(info.arena_elems) * 8)
+            ms = C.c_float()
+            check(lib.tadev_elementwise_eval(handle, arena.ptr, C.byref(ms)))
+            ElementwiseEngine.last_ms = ms.value
+        finally:
+            lib.tadev_elementwise_destroy(handle)
+        own = self.a.array._owner if w.size > 1 else (lambda o: 0)
+        Cres.release()  # the old tiles (possibly operands of this expression: stream-ordered free after the kernel)
+        Cres.trange, Cres.shape, Cres._arena = tr, shape, arena
+        Cres.tiles = {o_: DeviceBuffer(dev, arena.ptr + f_ * 8, e_ * 8, False)
+                      for o_, f_, e_ in zip(ords.tolist(), offs.tolist(), elems.tolist())}
         Cres._owner = own
 
 
