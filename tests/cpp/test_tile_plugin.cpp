@@ -7,6 +7,7 @@
 // Runs on a GPU box only (tests/test_gpu_cpp_plugin.py).
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "tadev.hpp"
@@ -108,6 +109,39 @@ int main() {
     bool ok = true;
     for (size_t i = 0; i < in.size(); ++i) ok = ok && out[i] == 2.0 * in[i];
     CHECK(ok);
+  }
+  // MADWorld-style concurrency (SURVEY §8 b / a10): pool threads call the tile ops concurrently, each
+  // task on the stream of its result (stream_for(ordinal)); the ABI promises thread-safety for
+  // concurrent calls, including calls that share a stream (descriptor staging ring, tensor-map cache).
+  {
+    const int nthreads = 8, ntasks = 24, dim = 96;  // even, 16-byte aligned rows -> the TMA fast path
+    const auto X = int_matrix(dim, dim, 7), Y = int_matrix(dim, dim, 8);
+    std::vector<double> want((size_t)dim * dim, 0.0);
+    for (int i = 0; i < dim; ++i) for (int j = 0; j < dim; ++j) { double s2 = 0; for (int x = 0; x < dim; ++x) s2 += X[(size_t)i * dim + x] * Y[(size_t)x * dim + j]; want[(size_t)i * dim + j] = s2; }
+    Tile tx(ctx, {dim, dim}), ty(ctx, {dim, dim});
+    tx.from_host(X.data());
+    ty.from_host(Y.data());
+    std::vector<int> bad(nthreads, 0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&, t] {
+        GemmHelper h(Op::NoTrans, Op::NoTrans, 2u, 2u, 2u);
+        std::vector<double> got((size_t)dim * dim);
+        for (int task = t; task < ntasks; task += nthreads) {
+          Tile acc(ctx, {dim, dim}, (uint64_t)task);   // stream = task % nstreams: several threads share a stream
+          const int reps = 1 + task % 3;
+          Tile first = gemm(tx, ty, 1.0, h);
+          Tile sum = clone(first);
+          for (int r = 1; r < reps; ++r) gemm(sum, tx, ty, 1.0, h);  // reduce-pair accumulation
+          Tile p = permute(sum, {1, 0});
+          p.to_host(got.data());
+          for (int i = 0; i < dim; ++i) for (int j = 0; j < dim; ++j) if (got[(size_t)j * dim + i] != reps * want[(size_t)i * dim + j]) bad[t]++;
+        }
+      });
+    for (auto& th : pool) th.join();
+    int nbad = 0;
+    for (int b : bad) nbad += b;
+    CHECK(nbad == 0);
   }
   ctx.sync();
   std::printf(failures ? "CPP_PLUGIN FAILED (%d)\n" : "CPP_PLUGIN OK\n", failures);

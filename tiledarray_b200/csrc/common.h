@@ -6,6 +6,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -41,6 +43,7 @@ struct StagingRing {
   size_t cap[kSlots] = {0, 0, 0, 0};
   cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t uploaded[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  bool busy[kSlots] = {false, false, false, false};  // leased to a caller that has not recorded `done` yet
   int next = 0;
 };
 
@@ -53,7 +56,8 @@ struct tadev_ctx {
   cudaStream_t desc_stream = nullptr;  // descriptor uploads: never queued behind a caller stream's pending work
   std::atomic<int64_t> launches{0};
   std::mutex mu;  // guards staging rings
-  std::vector<std::pair<cudaStream_t, StagingRing>> staging;
+  std::condition_variable stage_cv;  // a leased staging slot was released
+  std::vector<std::pair<cudaStream_t, std::unique_ptr<StagingRing>>> staging;
   // communicators
   ncclComm* world = nullptr;
   ncclComm* row_comm = nullptr;  // ranks sharing my grid row   (A column-panels travel here)
@@ -65,10 +69,28 @@ struct tadev_ctx {
   void* tmap_cache = nullptr;       // TmapCache (gemm_f64_ws.cu): per-tile CUtensorMaps in device memory
 };
 
-// Obtain a staging slot of at least `bytes` for stream s. Returns host + device pointers; the
-// caller memcpyAsync's h->d on s and then records `*done` on s after the consuming kernel.
-int tadev_stage(tadev_ctx* ctx, cudaStream_t s, size_t bytes, void** h, void** d, cudaEvent_t* done,
-                cudaEvent_t* uploaded = nullptr);
+// A leased staging slot of at least `bytes` for stream s: pinned host + device buffers for one
+// descriptor block. acquire() waits (under the ctx lock) for a slot that no other thread holds, then
+// — outside the lock — for the kernel that last consumed that slot. release() (also run by the
+// destructor, so every early return is covered) records `done` on the stream AFTER the consuming
+// kernel was enqueued and only then hands the slot back: concurrent callers that share a stream
+// (MADWorld pool threads, stream_for(ordinal)) can therefore never overwrite a block that another
+// thread is still filling or has not launched yet.
+struct StageLease {
+  tadev_ctx* ctx = nullptr;
+  cudaStream_t s = nullptr;
+  StagingRing* ring = nullptr;
+  int slot = -1;
+  void* h = nullptr;
+  void* d = nullptr;
+  cudaEvent_t done = nullptr, uploaded = nullptr;
+  int acquire(tadev_ctx* ctx, cudaStream_t s, size_t bytes);
+  void release();
+  ~StageLease() { release(); }
+  StageLease() = default;
+  StageLease(const StageLease&) = delete;
+  StageLease& operator=(const StageLease&) = delete;
+};
 // Upload a staged descriptor block on the ctx's descriptor stream and make `s` wait for it. Enqueued
 // on `s` itself the copy would only be issued when the previous kernel of `s` finishes — the moment the
 // SUMMA driver's next multi-GB panel upload grabs the H2D copy engine — and the next GEMM would start a

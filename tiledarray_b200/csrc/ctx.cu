@@ -68,10 +68,10 @@ extern "C" int tadev_finalize(tadev_ctx* ctx) {
   tadev_tmap_cache_destroy(ctx);
   for (auto& pr : ctx->staging) {
     for (int i = 0; i < StagingRing::kSlots; ++i) {
-      if (pr.second.h[i]) cudaFreeHost(pr.second.h[i]);
-      if (pr.second.d[i]) cudaFree(pr.second.d[i]);
-      if (pr.second.done[i]) cudaEventDestroy(pr.second.done[i]);
-      if (pr.second.uploaded[i]) cudaEventDestroy(pr.second.uploaded[i]);
+      if (pr.second->h[i]) cudaFreeHost(pr.second->h[i]);
+      if (pr.second->d[i]) cudaFree(pr.second->d[i]);
+      if (pr.second->done[i]) cudaEventDestroy(pr.second->done[i]);
+      if (pr.second->uploaded[i]) cudaEventDestroy(pr.second->uploaded[i]);
     }
   }
   for (auto s : ctx->streams) cudaStreamDestroy(s);
@@ -186,31 +186,60 @@ int tadev_stage_upload(tadev_ctx* ctx, cudaStream_t s, void* d, const void* h, s
   return TADEV_OK;
 }
 
-int tadev_stage(tadev_ctx* ctx, cudaStream_t s, size_t bytes, void** h, void** d, cudaEvent_t* done, cudaEvent_t* uploaded) {
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  StagingRing* ring = nullptr;
-  for (auto& pr : ctx->staging)
-    if (pr.first == s) ring = &pr.second;
-  if (!ring) {
-    ctx->staging.emplace_back(s, StagingRing());
-    ring = &ctx->staging.back().second;
+int StageLease::acquire(tadev_ctx* ctx_, cudaStream_t s_, size_t bytes) {
+  release();
+  ctx = ctx_; s = s_;
+  int i = -1;
+  {
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    for (auto& pr : ctx->staging)
+      if (pr.first == s) ring = pr.second.get();
+    if (!ring) {
+      ctx->staging.emplace_back(s, std::unique_ptr<StagingRing>(new StagingRing()));
+      ring = ctx->staging.back().second.get();
+    }
+    StagingRing* rg = ring;
+    auto free_slot = [rg]() {
+      for (int n = 0; n < StagingRing::kSlots; ++n) {
+        const int c = (rg->next + n) % StagingRing::kSlots;
+        if (!rg->busy[c]) return c;
+      }
+      return -1;
+    };
+    ctx->stage_cv.wait(lk, [&] { return free_slot() >= 0; });
+    i = free_slot();
+    ring->busy[i] = true;
+    ring->next = (i + 1) % StagingRing::kSlots;
   }
-  int i = ring->next;
-  ring->next = (ring->next + 1) % StagingRing::kSlots;
+  slot = i;  // from here on the slot is ours: no lock needed
   if (!ring->done[i]) TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&ring->done[i], cudaEventDisableTiming));
-  else TADEV_CHECK_CUDA(cudaEventSynchronize(ring->done[i]));  // previous user of this slot finished
+  else TADEV_CHECK_CUDA(cudaEventSynchronize(ring->done[i]));  // the kernel that last read this slot finished
+  if (!ring->uploaded[i]) TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&ring->uploaded[i], cudaEventDisableTiming));
   if (ring->cap[i] < bytes) {
     size_t cap = bytes + bytes / 2 + 4096;
     if (ring->h[i]) TADEV_CHECK_CUDA(cudaFreeHost(ring->h[i]));
     if (ring->d[i]) TADEV_CHECK_CUDA(cudaFree(ring->d[i]));
+    ring->h[i] = ring->d[i] = nullptr;
+    ring->cap[i] = 0;
     TADEV_CHECK_CUDA(cudaMallocHost(&ring->h[i], cap));
     TADEV_CHECK_CUDA(cudaMalloc(&ring->d[i], cap));
     ring->cap[i] = cap;
   }
-  if (!ring->uploaded[i]) TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&ring->uploaded[i], cudaEventDisableTiming));
-  *h = ring->h[i];
-  *d = ring->d[i];
-  *done = ring->done[i];
-  if (uploaded) *uploaded = ring->uploaded[i];
+  h = ring->h[i];
+  d = ring->d[i];
+  done = ring->done[i];
+  uploaded = ring->uploaded[i];
   return TADEV_OK;
+}
+
+void StageLease::release() {
+  if (slot < 0 || !ring) return;
+  if (ring->done[slot]) cudaEventRecord(ring->done[slot], s);  // after the consuming kernel in stream order
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ring->busy[slot] = false;
+  }
+  ctx->stage_cv.notify_all();
+  slot = -1;
+  ring = nullptr;
 }

@@ -64,10 +64,10 @@ extern "C" int tadev_tiles_binary_f64(tadev_ctx* ctx, tadev_stream s_, int op, i
   cudaStream_t s = (cudaStream_t)s_;
   for (int first = 0; first < ntiles; first += 32768) {  // gridDim.y limit
     const int n = std::min(32768, ntiles - first);
-    void *h = nullptr, *d = nullptr;
-    cudaEvent_t done;
-    int rc = tadev_stage(ctx, s, sizeof(TileOp) * (size_t)n, &h, &d, &done);
+    StageLease L;
+    int rc = L.acquire(ctx, s, sizeof(TileOp) * (size_t)n);
     if (rc) return rc;
+    void *h = L.h, *d = L.d;
     TileOp* ops = static_cast<TileOp*>(h);
     int64_t maxn = 0;
     for (int i = 0; i < n; ++i) {
@@ -85,7 +85,6 @@ extern "C" int tadev_tiles_binary_f64(tadev_ctx* ctx, tadev_stream s_, int op, i
     else tiles_binary_kernel<TADEV_EW_MULT><<<grid, 256, 0, s>>>(static_cast<const TileOp*>(d), alpha, beta);
     ctx->launches++;
     TADEV_CHECK_CUDA(cudaGetLastError());
-    TADEV_CHECK_CUDA(cudaEventRecord(done, s));
-  }
+  }  // ~StageLease records `done` after the launch and returns the slot
   return TADEV_OK;
 }

@@ -320,10 +320,10 @@ extern "C" int tadev_gemm_grouped_f64(tadev_ctx* ctx, tadev_stream s_, int opA, 
   const size_t pb = sizeof(int32_t) * (size_t)(ngroups + 1);
   const size_t off_t = (gb + 15) & ~size_t(15);
   const size_t off_p = (off_t + tb + 15) & ~size_t(15);
-  void *h = nullptr, *d = nullptr;
-  cudaEvent_t done;
-  int rc = tadev_stage(ctx, s, off_p + pb, &h, &d, &done);
+  StageLease L;
+  int rc = L.acquire(ctx, s, off_p + pb);
   if (rc) return rc;
+  void *h = L.h, *d = L.d;
   memcpy(h, h_groups, gb);
   if (tb) memcpy((char*)h + off_t, h_tasks, tb);
   memcpy((char*)h + off_p, prefix.data(), pb);
@@ -331,8 +331,7 @@ extern "C" int tadev_gemm_grouped_f64(tadev_ctx* ctx, tadev_stream s_, int opA, 
   rc = launch_gemm_grouped_f64(ctx, s, opA, opB, alpha, (const tadev_gemm_group*)d, ngroups,
                                (const tadev_gemm_task*)((char*)d + off_t), (const int32_t*)((char*)d + off_p),
                                (int)total, al);
-  TADEV_CHECK_CUDA(cudaEventRecord(done, s));
-  return rc;
+  return rc;  // ~StageLease records `done` after the launch and returns the slot
 }
 
 extern "C" int tadev_gemm_grouped_f64_dev(tadev_ctx* ctx, tadev_stream s, int opA, int opB, double alpha,

@@ -593,10 +593,11 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
   const size_t off_t = (gb + 15) & ~size_t(15);
   const size_t off_p = (off_t + tb + 15) & ~size_t(15);
   const size_t off_c = (off_p + pb + 15) & ~size_t(15);
-  void *h = nullptr, *d = nullptr;
-  cudaEvent_t done, uploaded;
-  int rc = tadev_stage(ctx, s, off_c + 16, &h, &d, &done, &uploaded);
+  StageLease L;
+  int rc = L.acquire(ctx, s, off_c + 16);
   if (rc) return rc;
+  void *h = L.h, *d = L.d;
+  cudaEvent_t uploaded = L.uploaded;
   memcpy(h, h_groups, gb);
   rc = resolve_maps(ctx, opA, opB, h_groups, ngroups, h_tasks, (WsTask*)((char*)h + off_t));
   if (rc) return rc;
@@ -636,6 +637,5 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
     case 3: rc = launch_ws_variant<1, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched, wave_sync); break;
     default: tadev_set_error("launch_gemm_grouped_f64_ws: bad op flags %d %d", opA, opB); rc = TADEV_EINVAL;
   }
-  TADEV_CHECK_CUDA(cudaEventRecord(done, s));
-  return rc;
+  return rc;  // ~StageLease records `done` after the launch and returns the slot
 }

@@ -450,17 +450,16 @@ extern "C" int tadev_permute_batched(tadev_ctx* ctx, tadev_stream s_, int rank, 
   }
   for (int first = 0; first < ntiles; first += 32768) {  // gridDim.y limit
     const int n = std::min(32768, ntiles - first);
-    void *h = nullptr, *d = nullptr;
-    cudaEvent_t done;
-    rc = tadev_stage(ctx, s, sizeof(void*) * 2 * (size_t)n, &h, &d, &done);
+    StageLease L;
+    rc = L.acquire(ctx, s, sizeof(void*) * 2 * (size_t)n);
     if (rc) return rc;
+    void *h = L.h, *d = L.d;
     memcpy(h, h_in + first, sizeof(void*) * n);
     memcpy((char*)h + sizeof(void*) * n, h_out + first, sizeof(void*) * n);
     TADEV_CHECK_CUDA(cudaMemcpyAsync(d, h, sizeof(void*) * 2 * (size_t)n, cudaMemcpyHostToDevice, s));
     rc = launch_plan(ctx, s, plan, al16, nullptr, nullptr, (const void* const*)d, (void* const*)((char*)d + sizeof(void*) * n), n);
-    TADEV_CHECK_CUDA(cudaEventRecord(done, s));
     if (rc) return rc;
-  }
+  }  // ~StageLease records `done` after the launch and returns the slot
   return TADEV_OK;
 }
 
