@@ -311,7 +311,9 @@ int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_st
  * tile permutations around Summa (dist_eval/array_eval.h:42,170; contract_reduce.h:370-378).
  * The caller describes the two argument arrays; `create` plans the contraction (optionally
  * exchanging the operands), derives the result tiling, screens the result shape on the device and
- * lays out the local result tiles; `eval` runs it into a caller-provided arena. This is what a
+ * lays out the local result tiles; `eval` runs it into a caller-provided arena. Indices shared by both
+ * arguments AND kept in the target make a general (fused-index, batched) product (cont_engine.h:679-1100,
+ * tile_op/batched_contract_reduce.h, SparseShape::gemm_batched): one grouped-GEMM launch, single rank. This is what a
  * TA::DistArray-level binding calls for `c("i,j") = a("i,k") * b("k,j")` (include/tiledarray.hpp,
  * tiledarray_b200/tiledarray.py). */
 #define TADEV_MEM_DEVICE 0

@@ -336,6 +336,53 @@ def test_elementwise_expressions_sparse_and_truncate(world):
         t.release()
 
 
+@pytest.mark.parametrize("target,lidx,ridx", [
+    ("b,i,j", "b,i,k", "b,k,j"),          # canonical batched GEMM
+    ("i,b,j", "i,k,b", "k,b,j"),          # every array needs a permutation
+    ("b,i,j", "b,i", "b,j"),              # batched outer product (nothing contracted)
+    ("b", "b,k", "b,k"),                  # no external index: row-wise dot products
+    ("b,c,i", "c,b,i,k", "b,k,c"),        # two fused indices, right operand has no external index
+])
+def test_general_products_dense(world, target, lidx, ridx):
+    """General products (fused + contracted + free indices; TensorProduct::General, cont_engine.h:679-1100,
+    BatchedContractReduce): the fused indices are batch indices of one grouped-GEMM launch. Exact (int)."""
+    rng = np.random.default_rng(len(target) * 13 + len(lidx))
+    dims = {"b": TiledRange1(0, 3, 5), "c": TiledRange1(0, 2, 6), "i": TiledRange1(0, 4, 10), "j": TiledRange1(0, 6, 8, 14),
+            "k": TiledRange1(0, 2, 8, 12)}
+    trL = _tr(*[dims[x] for x in lidx.split(",")])
+    trR = _tr(*[dims[x] for x in ridx.split(",")])
+    trC = _tr(*[dims[x] for x in target.split(",")])
+    st = _check(world, target, lidx, ridx, trL, trR, trC)
+    assert st.nlaunches == 1
+    _check(world, target, lidx, ridx, trL, trR, trC, integer=False, factor=-0.75)
+
+
+def test_general_product_sparse_and_accumulate(world):
+    """Block-sparse general product: result shape = SparseShape::gemm_batched (sparse_shape.h:1707-1900), i.e. the
+    oracle's norm GEMM slab by slab, bit-exact; zero result tiles absent; c += accumulates."""
+    rng = np.random.default_rng(3)
+    db, di, dk, dj = TiledRange1(0, 3, 5, 9), TiledRange1(0, 4, 10), TiledRange1(0, 2, 8, 12), TiledRange1(0, 6, 8, 14)
+    trL, trR, trC = _tr(db, di, dk), _tr(db, dk, dj), _tr(db, di, dj)
+    (a, A, nA), (b, B, nB) = _sparse_pair(world, trL, trR, 0.5, rng)
+    c = DistArray(world, trC)
+    c["b,i,j"] = a["b,i,k"] * b["b,k,j"]
+    ref = np.einsum("bik,bkj->bij", A, B)
+    assert np.array_equal(c.to_numpy(), ref)
+    otrL = O.TiledRange(tuple(O.TiledRange1(d.bounds) for d in (db, di, dk)))
+    otrR = O.TiledRange(tuple(O.TiledRange1(d.bounds) for d in (db, dk, dj)))
+    oa, ob = O.SparseShape.from_tile_norms(nA, otrL), O.SparseShape.from_tile_norms(nB, otrR)
+    for h in range(db.ntiles):  # slab by slab: the folded (fused-mode-free) norm GEMM
+        sa = O.SparseShape(oa.norms[h], oa.size_vectors[1:], 0)
+        sb = O.SparseShape(ob.norms[h], ob.size_vectors[1:], 0)
+        want = sa.gemm(sb, 1.0, O.GemmHelper(0, 0, 2, 2, 2))
+        assert np.array_equal(c.shape.norms[h].view(np.uint32), want.norms.view(np.uint32)), h
+    assert sorted(c.tiles) == [o for o in range(trC.ntiles) if not c.shape.is_zero(o)]
+    c["b,i,j"] += 2.0 * (a["b,i,k"] * b["b,k,j"])
+    assert np.array_equal(c.to_numpy(), 3.0 * ref)
+    for x in (a, b, c):
+        x.release()
+
+
 def test_cont_errors(world):
     t, u = _uniform(8, 4), _uniform(8, 2)
     a = DistArray(world, _tr(t, t)).fill(1.0)

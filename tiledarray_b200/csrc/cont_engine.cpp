@@ -129,6 +129,10 @@ int copy_operand(const tadev_array_desc* a, Operand& o, const char* who) {
 
 }  // namespace
 
+namespace {
+std::vector<std::string> split_idx(const char* s);
+}
+
 struct tadev_contraction {
   tadev_ctx* ctx = nullptr;
   tadev_contract_options opt{};
@@ -139,6 +143,11 @@ struct tadev_contraction {
   int lo[2], li[2], ro[2], ri[2];
   std::vector<int64_t> m_ext, n_ext, k_ext;
   int Mt = 0, Nt = 0, Kt = 0;
+  // general (fused + contracted + free indices) products: the leading `nh` modes of both operands and
+  // of the result are fused (batch) modes; Ht fused tile slabs, h_ext[h] batch elements in slab h
+  bool general = false;
+  int nh = 0, Ht = 1;
+  std::vector<int64_t> h_ext;
   TRange tr_gemm, tr_target;
   std::vector<int> perm_res;             // GEMM order -> target order (empty = identity)
   bool sparse = false;
@@ -208,8 +217,46 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
   E->factor = factor;
   if (options) E->opt = *options; else tadev_contract_options_default(&E->opt);
   int rc;
-  if (E->opt.exchange_operands) rc = tadev_plan_contraction_opt(target, left_idx, right_idx, &E->plan, &E->swapped);
-  else rc = tadev_plan_contraction(target, left_idx, right_idx, &E->plan);
+  {
+    // fused (Hadamard / batch) indices: present in both arguments AND kept in the target => general product
+    // (TensorProduct::General, expressions/cont_engine.h:679-1100, tile_op/batched_contract_reduce.h).
+    // Canonical layouts, as the reference's GeneralPermutationOptimizer produces them:
+    //   left (fused..., left outer..., contracted...)   right (fused..., contracted..., right outer...)
+    //   result (fused..., left outer..., right outer...);  anything else is permuted explicitly.
+    const auto T = split_idx(target), Li = split_idx(left_idx), Ri = split_idx(right_idx);
+    auto has = [](const std::vector<std::string>& v, const std::string& x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+    std::vector<std::string> Hh, oL, Kk, oR;
+    for (auto& x : Li) { if (has(Ri, x)) { if (has(T, x)) Hh.push_back(x); else Kk.push_back(x); } else oL.push_back(x); }
+    for (auto& x : Ri) if (!has(Li, x)) oR.push_back(x);
+    if (!Hh.empty()) {
+      TADEV_REQUIRE(!(Kk.empty() && oL.empty() && oR.empty()), "a pure Hadamard product is evaluated by the element-wise engine (tadev_elementwise_create)");
+      TADEV_REQUIRE(Li.size() <= 16 && Ri.size() <= 16 && T.size() <= 16, "general product: rank > 16");
+      std::vector<std::string> cL = Hh, cR = Hh, cRes = Hh;
+      cL.insert(cL.end(), oL.begin(), oL.end()); cL.insert(cL.end(), Kk.begin(), Kk.end());
+      cR.insert(cR.end(), Kk.begin(), Kk.end()); cR.insert(cR.end(), oR.begin(), oR.end());
+      cRes.insert(cRes.end(), oL.begin(), oL.end()); cRes.insert(cRes.end(), oR.begin(), oR.end());
+      TADEV_REQUIRE(T.size() == cRes.size(), "general product: target rank %zu != result rank %zu", T.size(), cRes.size());
+      for (auto& x : cRes) TADEV_REQUIRE(has(T, x), "general product: result index '%s' is not in the target", x.c_str());
+      tadev_contraction_plan& G = E->plan;
+      memset(&G, 0, sizeof(G));
+      G.left_rank = (int32_t)Li.size(); G.right_rank = (int32_t)Ri.size(); G.result_rank = (int32_t)cRes.size();
+      G.inner_rank = (int32_t)Kk.size(); G.opA = G.opB = TADEV_OP_N; G.left_permtype = G.right_permtype = 1;
+      for (int i = 0; i < 16; ++i) G.perm_left[i] = G.perm_right[i] = G.perm_result[i] = -1;
+      auto image = [](const std::vector<std::string>& from, const std::vector<std::string>& to, int32_t* perm) {
+        bool ident = true;
+        for (size_t i = 0; i < from.size(); ++i) ident = ident && from[i] == to[i];
+        if (ident) return;
+        for (size_t i = 0; i < from.size(); ++i) perm[i] = (int32_t)(std::find(to.begin(), to.end(), from[i]) - to.begin());
+      };
+      image(Li, cL, G.perm_left); image(Ri, cR, G.perm_right); image(cRes, T, G.perm_result);
+      if (G.perm_left[0] >= 0) G.left_permtype = 3;
+      if (G.perm_right[0] >= 0) G.right_permtype = 3;
+      E->general = true;
+      E->nh = (int)Hh.size();
+      rc = TADEV_OK;
+    } else if (E->opt.exchange_operands) rc = tadev_plan_contraction_opt(target, left_idx, right_idx, &E->plan, &E->swapped);
+    else rc = tadev_plan_contraction(target, left_idx, right_idx, &E->plan);
+  }
   if (rc) return rc;
   const tadev_contraction_plan& P = E->plan;
   if ((rc = copy_operand(E->swapped ? right : left, E->L, "tadev_contraction_create(left)"))) return rc;
@@ -229,6 +276,18 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
   if (P.opB == TADEV_OP_N) { E->ri[0] = 0; E->ri[1] = E->ro[0] = nc; E->ro[1] = rr; }
   else { E->ro[0] = 0; E->ro[1] = E->ri[0] = rr - nc; E->ri[1] = rr; }
   const TRange &trA = E->L.ptr, &trB = E->R.ptr;
+  if (E->general) {
+    // ranges in the canonical layouts: left (H, outer, K), right (H, K, outer)
+    const int nh = E->nh;
+    TADEV_REQUIRE(E->L.d.memory == TADEV_MEM_DEVICE && E->R.d.memory == TADEV_MEM_DEVICE, "general products take device-resident arrays");
+    TADEV_REQUIRE(ctx->nranks == 1, "general (fused-index) products are evaluated on one rank in this version");
+    E->lo[0] = nh; E->lo[1] = E->li[0] = lr - nc; E->li[1] = lr;
+    E->ri[0] = nh; E->ri[1] = E->ro[0] = nh + nc; E->ro[1] = rr;
+    for (int d = 0; d < nh; ++d) TADEV_REQUIRE(trA.b[d] == trB.b[d], "general product: the fused tiled ranges are not congruent");
+    E->h_ext = fused_ext(trA, 0, nh);
+    E->Ht = (int)E->h_ext.size();
+    for (int d = 0; d < nh; ++d) E->tr_gemm.b.push_back(trA.b[d]);
+  }
   for (int d = 0; d < nc; ++d)
     TADEV_REQUIRE(trA.b[E->li[0] + d] == trB.b[E->ri[0] + d], "contraction: inner tiled ranges are not congruent");
   E->m_ext = fused_ext(trA, E->lo[0], E->lo[1]);
@@ -252,16 +311,33 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
     TADEV_REQUIRE(!E->L.dense() && !E->R.dense(), "mixed dense/sparse contraction is not supported");
     const int Mt = E->Mt, Nt = E->Nt, Kt = E->Kt;
     // 2-D views in GEMM orientation
-    E->a_n.resize((size_t)Mt * Kt);
-    E->b_n.resize((size_t)Kt * Nt);
+    E->a_n.resize((size_t)E->Ht * Mt * Kt);
+    E->b_n.resize((size_t)E->Ht * Kt * Nt);
     if (P.opA == TADEV_OP_N) E->a_n = E->L.pnorms;
     else for (int k = 0; k < Kt; ++k) for (int i = 0; i < Mt; ++i) E->a_n[(size_t)i * Kt + k] = E->L.pnorms[(size_t)k * Mt + i];
     if (P.opB == TADEV_OP_N) E->b_n = E->R.pnorms;
     else for (int j = 0; j < Nt; ++j) for (int k = 0; k < Kt; ++k) E->b_n[(size_t)k * Nt + j] = E->R.pnorms[(size_t)j * Kt + k];
     std::vector<float> ksz;
     if (nc > 0) ksz = recursive_outer(trA, E->li[0], E->li[1]);
-    rc = device_shape_gemm(ctx, Mt, Nt, nc > 0 ? Kt : 0, E->a_n, E->b_n, ksz, (float)std::fabs(factor), thr, E->c_n, &E->nzero);
-    if (rc) return rc;
+    if (!E->general) {
+      rc = device_shape_gemm(ctx, Mt, Nt, nc > 0 ? Kt : 0, E->a_n, E->b_n, ksz, (float)std::fabs(factor), thr, E->c_n, &E->nzero);
+      if (rc) return rc;
+    } else {
+      // SparseShape::gemm_batched (sparse_shape.h:1707-1900): every fused-index slab is a norm GEMM with the
+      // same contracted-size scaling (or a per-slab outer product when nothing is contracted)
+      E->c_n.assign((size_t)E->Ht * Mt * Nt, 0.0f);
+      E->nzero = 0;
+      std::vector<float> as((size_t)Mt * Kt), bs((size_t)Kt * Nt), cs;
+      for (int h = 0; h < E->Ht; ++h) {
+        std::copy(E->a_n.begin() + (size_t)h * Mt * Kt, E->a_n.begin() + (size_t)(h + 1) * Mt * Kt, as.begin());
+        std::copy(E->b_n.begin() + (size_t)h * Kt * Nt, E->b_n.begin() + (size_t)(h + 1) * Kt * Nt, bs.begin());
+        uint64_t nz = 0;
+        rc = device_shape_gemm(ctx, Mt, Nt, nc > 0 ? Kt : 0, as, bs, ksz, (float)std::fabs(factor), thr, cs, &nz);
+        if (rc) return rc;
+        std::copy(cs.begin(), cs.end(), E->c_n.begin() + (size_t)h * Mt * Nt);
+        E->nzero += nz;
+      }
+    }
     E->target_norms = E->perm_res.empty() ? E->c_n : permute_norms(E->c_n, E->tr_gemm.tiles_shape(), E->perm_res);
   }
 
@@ -281,11 +357,12 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
     const std::vector<int64_t> gshape = E->tr_gemm.tiles_shape(), tshape = E->tr_target.tiles_shape();
     std::vector<int64_t> gidx, tidx(gshape.size());
     int64_t off = 0;
+    for (int h = 0; h < E->Ht; ++h)
     for (int i = E->r; i < E->Mt; i += E->Pr)
       for (int j = E->c; j < E->Nt; j += E->Pc) {
-        const int64_t key = (int64_t)i * E->Nt + j;
+        const int64_t key = ((int64_t)h * E->Mt + i) * E->Nt + j;  // ordinal in the GEMM-order tile grid (H, M, N)
         if (E->sparse && E->c_n[key] < thr) continue;
-        const int64_t e = E->m_ext[i] * E->n_ext[j];
+        const int64_t e = (E->general ? E->h_ext[h] : 1) * E->m_ext[i] * E->n_ext[j];
         E->keys.push_back(key); E->elems.push_back(e); E->offs.push_back(off);
         off += (e + 1) & ~(int64_t)1;
         if (E->perm_res.empty()) E->target_ord.push_back(key);
@@ -370,7 +447,8 @@ inline size_t fused_pos(int64_t po, bool op_n, int64_t rows, int64_t cols) {
 int build_view(tadev_contraction* E, Operand& o, bool is_left, View& v, float* permute_ms_acc) {
   tadev_ctx* ctx = E->ctx;
   const bool op_n = (is_left ? E->plan.opA : E->plan.opB) == TADEV_OP_N;
-  const int64_t rows = is_left ? E->Mt : E->Kt, cols = is_left ? E->Kt : E->Nt;
+  // general products: the fused slabs are the leading (slowest) part of the row index
+  const int64_t rows = (int64_t)(E->general ? E->Ht : 1) * (is_left ? E->Mt : E->Kt), cols = is_left ? E->Kt : E->Nt;
   v.table.assign((size_t)std::max<int64_t>(rows * cols, 1), nullptr);
   const int64_t n = o.tr.total();
   const float thr = E->opt.threshold;
@@ -410,7 +488,7 @@ int build_view(tadev_contraction* E, Operand& o, bool is_left, View& v, float* p
     for (int d = 0; d < R; ++d) { exts.push_back(o.tr.ext(d, idx[d])); vol *= exts.back(); }
     bytes += vol * 8;
   }
-  bool stream = E->opt.stream_permutes > 0 || (E->opt.stream_permutes < 0 && bytes > E->opt.stream_permute_bytes);
+  bool stream = !E->general && (E->opt.stream_permutes > 0 || (E->opt.stream_permutes < 0 && bytes > E->opt.stream_permute_bytes));
   if (stream) {
     v.lazy = true;
     v.provider = tadev_provider_permute;
@@ -488,9 +566,49 @@ extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, 
     rc = tadev_alloc(ctx, (size_t)E->arena_elems * 8, (void**)&gemm_arena, s);
     if (rc) return rc;
   }
-  std::vector<double*> c_tab((size_t)std::max<int64_t>((int64_t)E->Mt * E->Nt, 1), nullptr);
+  std::vector<double*> c_tab((size_t)std::max<int64_t>((int64_t)E->Ht * E->Mt * E->Nt, 1), nullptr);
   for (size_t t = 0; t < E->keys.size(); ++t) c_tab[E->keys[t]] = gemm_arena + E->offs[t];
 
+  tadev_summa_stats st{};
+  if (E->general) {
+    // BatchedContractReduce (tile_op/batched_contract_reduce.h) for every result tile of every fused slab,
+    // in ONE grouped launch: batch element e of tile (h,i,j) is its own group — C + e*m*n accumulates
+    // A(h,i,k)[e] * B(h,k,j)[e] over the contracted tiles k (a tile (nb, m, k) is nb row-major m x k matrices).
+    TADEV_REQUIRE(result_memory == TADEV_MEM_DEVICE, "general products produce device-resident results");
+    std::vector<tadev_gemm_group> groups;
+    std::vector<tadev_gemm_task> tasks;
+    const float thr = E->opt.threshold;
+    const int Mt = E->Mt, Nt = E->Nt, Kt = E->Kt;
+    for (size_t t = 0; t < E->keys.size(); ++t) {
+      const int64_t key = E->keys[t];
+      const int h = (int)(key / ((int64_t)Mt * Nt)), i = (int)((key / Nt) % Mt), j = (int)(key % Nt);
+      const int64_t m = E->m_ext[i], n = E->n_ext[j], nb = E->h_ext[h];
+      for (int64_t e = 0; e < nb; ++e) {
+        tadev_gemm_group G{c_tab[key] + e * m * n, (int32_t)m, (int32_t)n, (int32_t)tasks.size(), 0, accumulate ? 1 : 0, 0};
+        for (int k = 0; k < Kt; ++k) {
+          const size_t ak = ((size_t)h * Mt + i) * Kt + k, bk = ((size_t)h * Kt + k) * Nt + j;
+          if (E->sparse && (E->a_n[ak] < thr || E->b_n[bk] < thr)) continue;
+          const double *At = vA.table[ak], *Bt = vB.table[bk];
+          TADEV_REQUIRE(At && Bt, "general product: argument tile (%d,%d,%d) has no data", h, i, k);
+          const int64_t kk = E->k_ext[k];
+          tasks.push_back({At + e * m * kk, Bt + e * kk * n, (int32_t)kk, 0});
+          if (e == 0) { ++st.npairs; st.flops += 2.0 * (double)nb * (double)m * (double)n * (double)kk; }
+        }
+        G.task_end = (int32_t)tasks.size();
+        groups.push_back(G);
+        TADEV_REQUIRE(tasks.size() < (size_t)1 << 30 && groups.size() < (size_t)1 << 30, "general product: too many batch tasks for one launch");
+      }
+    }
+    void *e0 = nullptr, *e1 = nullptr;
+    tadev_event_create(ctx, &e0); tadev_event_create(ctx, &e1);
+    tadev_event_record(ctx, e0, s);
+    rc = tadev_gemm_grouped_f64(ctx, s, TADEV_OP_N, TADEV_OP_N, E->factor, groups.data(), (int)groups.size(), tasks.data(), (int)tasks.size());
+    tadev_event_record(ctx, e1, s);
+    float ms = 0;
+    tadev_event_elapsed_ms(ctx, e0, e1, &ms);
+    tadev_event_destroy(ctx, e0); tadev_event_destroy(ctx, e1);
+    st.nsteps = Kt; st.nlaunches = groups.empty() ? 0 : 1; st.device_ms = ms; st.row_blocks = 1;
+  } else {
   tadev_summa_plan sp{};
   sp.Mt = E->Mt; sp.Nt = E->Nt; sp.Kt = E->Kt;
   sp.m_ext = E->m_ext.data(); sp.n_ext = E->n_ext.data(); sp.k_ext = E->k_ext.data();
@@ -506,8 +624,8 @@ extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, 
              (result_memory == TADEV_MEM_HOST ? TADEV_SUMMA_C_ON_HOST : 0) | (vA.lazy ? TADEV_SUMMA_A_LAZY : 0) | (vB.lazy ? TADEV_SUMMA_B_LAZY : 0);
   if (vA.lazy) { sp.a_provider = vA.provider; sp.a_user = vA.user(); }
   if (vB.lazy) { sp.b_provider = vB.provider; sp.b_user = vB.user(); }
-  tadev_summa_stats st{};
   rc = tadev_summa_f64(ctx, &sp, &st);
+  }
   if (vA.tmp_arena) tadev_free(ctx, vA.tmp_arena, s);
   if (vB.tmp_arena) tadev_free(ctx, vB.tmp_arena, s);
   if (rc) { if (gemm_arena != result_arena) tadev_free(ctx, gemm_arena, s); return rc; }
