@@ -222,6 +222,13 @@ int tadev_plan_contraction_opt(const char* target, const char* left, const char*
 int tadev_comm_unique_id(void* out128);
 int tadev_comm_init(tadev_ctx* ctx, const void* unique_id128, int rank, int nranks, int Pr, int Pc);
 int tadev_comm_destroy(tadev_ctx* ctx);
+/* Point-to-point redistribution of tiles over the world communicator: this rank sends nsend tiles and
+ * receives nrecv. Both lists are derived by every rank from replicated metadata and must be in the same
+ * relative order on the two sides of every (sender, receiver) pair (e.g. ascending tile ordinal).
+ * h_* are host arrays; pointers are device pointers. One NCCL group. */
+int tadev_exchange_tiles(tadev_ctx* ctx, tadev_stream s, int nsend, const void* const* h_src, const size_t* h_sbytes,
+                         const int32_t* h_dst_rank, int nrecv, void* const* h_dst, const size_t* h_rbytes,
+                         const int32_t* h_src_rank);
 /* which=0: row communicator (A panels), which=1: column communicator (B panels). */
 int tadev_bcast_panel(tadev_ctx* ctx, tadev_stream s, int which, int root, void* d_buf, size_t bytes);
 
@@ -328,6 +335,10 @@ typedef struct {
   const void* const* tiles;  /* [prod ntiles] tile pointers; NULL entry = zero or not local. Lazy arrays: NULL
                                 table = every non-zero tile is local, else non-NULL entries mark local tiles */
   uint64_t lazy_seed;
+  const int32_t* owners;     /* [prod ntiles] rank that holds each tile (the array's process map), or NULL. With
+                                owners, a multi-rank contraction redistributes device tiles that are not where SUMMA's
+                                cyclic maps need them (what ArrayEvalImpl does tile by tile, dist_eval/array_eval.h:170);
+                                without, every operand tile must already be local where it is needed. */
 } tadev_array_desc;
 
 typedef struct {

@@ -628,6 +628,7 @@ class DistArray {
     std::vector<int64_t> bounds;
     std::vector<int32_t> ntiles;
     std::vector<const void*> table;
+    std::vector<int32_t> owners;
     explicit Desc(const DistArray& a) {
       const State& s = *a.st_;
       for (auto& dim : s.trange.data()) { ntiles.push_back((int32_t)dim.ntiles()); bounds.insert(bounds.end(), dim.bounds().begin(), dim.bounds().end()); }
@@ -641,6 +642,10 @@ class DistArray {
         for (int64_t o = 0; o < s.trange.ntiles(); ++o) if (a.is_local(o) && !a.is_zero(o)) table[o] = (const void*)1;
       } else table.assign(s.tiles.begin(), s.tiles.end());
       d.tiles = table.data();
+      if (s.world->size() > 1 && s.mem == Device) {  // the process map: lets the engine redistribute tiles
+        for (int64_t o = 0; o < s.trange.ntiles(); ++o) owners.push_back((int32_t)a.owner(o));
+        d.owners = owners.data();
+      }
     }
   };
   void allocate_() {

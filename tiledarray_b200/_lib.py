@@ -66,7 +66,8 @@ EW_AXPBY, EW_MULT = 0, 1
 
 class ArrayDescC(C.Structure):
     _fields_ = [("rank", C.c_int32), ("memory", C.c_int32), ("bounds", C.POINTER(C.c_int64)), ("ntiles", C.POINTER(C.c_int32)),
-                ("norms", C.POINTER(C.c_float)), ("tiles", C.POINTER(C.c_void_p)), ("lazy_seed", C.c_uint64)]
+                ("norms", C.POINTER(C.c_float)), ("tiles", C.POINTER(C.c_void_p)), ("lazy_seed", C.c_uint64),
+                ("owners", C.POINTER(C.c_int32))]
 
 
 class ContractOptionsC(C.Structure):
@@ -159,6 +160,7 @@ PROTOTYPES = {
     "tadev_comm_init": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "tadev_comm_destroy": (_i, [_vp]),
     "tadev_bcast_panel": (_i, [_vp, _vp, _i, _i, _vp, _sz]),
+    "tadev_exchange_tiles": (_i, [_vp, _vp, _i, _P(_vp), _P(_sz), _P(C.c_int32), _i, _P(_vp), _P(_sz), _P(C.c_int32)]),
     "tadev_summa_f64": (_i, [_vp, _P(SummaPlanC), _P(SummaStatsC)]),
     "tadev_provider_uniform": (_i, [_vp, _vp, _i, _P(_u64), _P(_vp), _P(_sz)]),
     "tadev_provider_permute": (_i, [_vp, _vp, _i, _P(_u64), _P(_vp), _P(_sz)]),

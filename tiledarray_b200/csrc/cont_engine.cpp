@@ -101,6 +101,10 @@ struct Operand {
   std::vector<int32_t> ntiles;
   std::vector<float> norms;           // empty = dense
   std::vector<const void*> tiles;     // empty: lazy array whose non-zero tiles are all local
+  std::vector<int32_t> owners;        // the array's process map (empty: unknown)
+  double* redist_arena = nullptr;     // tiles received by the redistribution (live during eval only)
+  std::vector<const void*> tiles_before;  // the caller's tile table, restored after eval
+  bool redistributed = false;
   std::vector<int> perm;              // explicit permutation (empty = none)
   TRange ptr;                         // permuted tiling
   std::vector<float> pnorms;          // permuted norms
@@ -123,6 +127,7 @@ int copy_operand(const tadev_array_desc* a, Operand& o, const char* who) {
   const int64_t n = o.tr.total();
   if (a->norms) o.norms.assign(a->norms, a->norms + n);
   if (a->tiles) o.tiles.assign(a->tiles, a->tiles + n);
+  if (a->owners) o.owners.assign(a->owners, a->owners + n);
   TADEV_REQUIRE(a->memory == TADEV_MEM_LAZY || a->tiles, "%s: null tile table", who);
   return TADEV_OK;
 }
@@ -418,6 +423,10 @@ extern "C" int tadev_contraction_owner(const tadev_contraction* E, int64_t targe
 }
 
 extern "C" int tadev_contraction_destroy(tadev_contraction* E) {
+  if (E) {
+    for (Operand* o : {&E->L, &E->R})
+      if (o->redist_arena) tadev_free(E->ctx, o->redist_arena, (tadev_stream)E->ctx->streams[0]);
+  }
   delete E;
   return TADEV_OK;
 }
@@ -442,6 +451,63 @@ struct View {
 inline size_t fused_pos(int64_t po, bool op_n, int64_t rows, int64_t cols) {
   // op N: the permuted tile grid is already [rows][cols]; op T: it is stored [cols][rows]
   return op_n ? (size_t)po : (size_t)((po % rows) * cols + po / rows);
+}
+
+// Redistribution: bring every non-zero tile of the operand to the rank SUMMA's cyclic maps want it on
+// (A(i,k) -> (i % Pr, k % Pc), B(k,j) -> (k % Pr, j % Pc) of the permuted, fused tile grid). Every rank
+// derives the same plan from the replicated shape + process map; tiles travel in ascending ordinal order.
+int redistribute_operand(tadev_contraction* E, Operand& o, bool is_left) {
+  tadev_ctx* ctx = E->ctx;
+  if (ctx->nranks == 1 || o.owners.empty() || o.redistributed || o.d.memory == TADEV_MEM_LAZY) return TADEV_OK;
+  const bool op_n = (is_left ? E->plan.opA : E->plan.opB) == TADEV_OP_N;
+  const int64_t rows = is_left ? E->Mt : E->Kt, cols = is_left ? E->Kt : E->Nt;
+  const int64_t n = o.tr.total();
+  const float thr = E->opt.threshold;
+  const int R = o.tr.rank(), me = ctx->rank;
+  const std::vector<int64_t> tshape = o.tr.tiles_shape(), pshape = o.ptr.tiles_shape();
+  std::vector<int64_t> idx, pidx(R);
+  std::vector<const void*> src;
+  std::vector<void*> dst;
+  std::vector<size_t> sbytes, rbytes;
+  std::vector<int32_t> to, from;
+  std::vector<int64_t> recv_ord, recv_off;
+  int64_t off = 0;
+  bool any_move = false;
+  std::vector<int32_t> need((size_t)n, -1);
+  for (int64_t ord = 0; ord < n; ++ord) {
+    if (!o.dense() && o.norms[ord] < thr) continue;
+    int64_t po = ord;
+    unravel(ord, tshape, idx);
+    if (!o.perm.empty()) { for (int i = 0; i < R; ++i) pidx[o.perm[i]] = idx[i]; po = ravel(pidx, pshape); }
+    const size_t pos = fused_pos(po, op_n, rows, cols);
+    const int64_t fr = (int64_t)pos / cols, fc = (int64_t)pos % cols;
+    need[ord] = (int32_t)((fr % E->Pr) * E->Pc + fc % E->Pc);
+    TADEV_REQUIRE(o.owners[ord] >= 0 && o.owners[ord] < ctx->nranks, "redistribution: tile %lld has owner %d", (long long)ord, o.owners[ord]);
+    if (need[ord] == o.owners[ord]) continue;
+    any_move = true;
+    size_t vol = 1;
+    for (int d = 0; d < R; ++d) vol *= (size_t)o.tr.ext(d, idx[d]);
+    if (o.owners[ord] == me) {
+      TADEV_REQUIRE(o.tiles[ord], "redistribution: tile %lld is owned by this rank but has no data", (long long)ord);
+      src.push_back(o.tiles[ord]); sbytes.push_back(vol * 8); to.push_back(need[ord]);
+    } else if (need[ord] == me) {
+      recv_ord.push_back(ord); recv_off.push_back(off); rbytes.push_back(vol * 8); from.push_back(o.owners[ord]);
+      off += (int64_t)((vol + 1) & ~(size_t)1);
+    }
+  }
+  o.redistributed = true;
+  if (!any_move) return TADEV_OK;  // same decision on every rank: the plan is built from replicated data
+  o.tiles_before = o.tiles;
+  TADEV_REQUIRE(o.d.memory == TADEV_MEM_DEVICE, "redistribution moves device-resident tiles only");
+  tadev_stream s = (tadev_stream)ctx->streams[0];
+  if (off > 0) { int rc = tadev_alloc(ctx, (size_t)off * 8, (void**)&o.redist_arena, s); if (rc) return rc; }
+  for (size_t t = 0; t < recv_ord.size(); ++t) dst.push_back(o.redist_arena + recv_off[t]);
+  int rc = tadev_exchange_tiles(ctx, s, (int)src.size(), src.data(), sbytes.data(), to.data(), (int)dst.size(), dst.data(), rbytes.data(), from.data());
+  if (rc) return rc;
+  // the effective local tile table: tiles that stayed, tiles that arrived; tiles that left are gone
+  for (int64_t ord = 0; ord < n; ++ord) if (need[ord] >= 0 && need[ord] != me) o.tiles[ord] = nullptr;
+  for (size_t t = 0; t < recv_ord.size(); ++t) o.tiles[recv_ord[t]] = dst[t];
+  return TADEV_OK;
 }
 
 int build_view(tadev_contraction* E, Operand& o, bool is_left, View& v, float* permute_ms_acc) {
@@ -555,7 +621,10 @@ extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, 
   if (stats) memset(stats, 0, sizeof(*stats));
   float permute_ms = 0.0f;
   View vA, vB;
-  int rc = build_view(E, E->L, true, vA, &permute_ms);
+  int rc = redistribute_operand(E, E->L, true);
+  if (!rc) rc = redistribute_operand(E, E->R, false);
+  if (rc) return rc;
+  rc = build_view(E, E->L, true, vA, &permute_ms);
   if (!rc) rc = build_view(E, E->R, false, vB, &permute_ms);
   if (rc) return rc;
 
@@ -666,6 +735,12 @@ extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, 
     permute_ms += ms;
     tadev_free(ctx, gemm_arena, s);
     if (rc) return rc;
+  }
+  // the received copies of redistributed operand tiles were only needed for this evaluation
+  for (Operand* o : {&E->L, &E->R}) {
+    if (o->redist_arena) { tadev_free(ctx, o->redist_arena, s); o->redist_arena = nullptr; }
+    if (!o->tiles_before.empty()) { o->tiles.swap(o->tiles_before); o->tiles_before.clear(); }
+    o->redistributed = false;
   }
   if (stats) { stats->summa = st; stats->permute_ms = permute_ms; }
   return TADEV_OK;

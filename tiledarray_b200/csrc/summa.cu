@@ -74,6 +74,26 @@ extern "C" int tadev_comm_destroy(tadev_ctx* ctx) {
   return TADEV_OK;
 }
 
+extern "C" int tadev_exchange_tiles(tadev_ctx* ctx, tadev_stream s, int nsend, const void* const* h_src, const size_t* h_sbytes,
+                                    const int32_t* h_dst_rank, int nrecv, void* const* h_dst, const size_t* h_rbytes,
+                                    const int32_t* h_src_rank) {
+  TADEV_REQUIRE(ctx && nsend >= 0 && nrecv >= 0, "tadev_exchange_tiles: bad args");
+  if (nsend == 0 && nrecv == 0) return TADEV_OK;
+  TADEV_REQUIRE(ctx->world, "tadev_exchange_tiles: communicators not initialised");
+  TADEV_REQUIRE((nsend == 0 || (h_src && h_sbytes && h_dst_rank)) && (nrecv == 0 || (h_dst && h_rbytes && h_src_rank)), "tadev_exchange_tiles: null arrays");
+  TADEV_CHECK_NCCL(ncclGroupStart());
+  for (int i = 0; i < nsend; ++i) {
+    TADEV_REQUIRE(h_dst_rank[i] >= 0 && h_dst_rank[i] < ctx->nranks && h_dst_rank[i] != ctx->rank, "tadev_exchange_tiles: bad destination rank");
+    if (h_sbytes[i]) TADEV_CHECK_NCCL(ncclSend(h_src[i], h_sbytes[i], ncclChar, h_dst_rank[i], ctx->world, (cudaStream_t)s));
+  }
+  for (int i = 0; i < nrecv; ++i) {
+    TADEV_REQUIRE(h_src_rank[i] >= 0 && h_src_rank[i] < ctx->nranks && h_src_rank[i] != ctx->rank, "tadev_exchange_tiles: bad source rank");
+    if (h_rbytes[i]) TADEV_CHECK_NCCL(ncclRecv(h_dst[i], h_rbytes[i], ncclChar, h_src_rank[i], ctx->world, (cudaStream_t)s));
+  }
+  TADEV_CHECK_NCCL(ncclGroupEnd());
+  return TADEV_OK;
+}
+
 extern "C" int tadev_bcast_panel(tadev_ctx* ctx, tadev_stream s, int which, int root, void* d_buf, size_t bytes) {
   TADEV_REQUIRE(ctx && (which == 0 || which == 1), "tadev_bcast_panel: bad args");
   ncclComm* comm = which == 0 ? ctx->row_comm : ctx->col_comm;

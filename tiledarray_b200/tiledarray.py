@@ -739,6 +739,11 @@ class ContEngine:
             table[ords] = np.fromiter((b_.ptr for b_ in arr.tiles.values()), dtype=np.uint64, count=len(arr.tiles))
         keep.append(table)
         d.tiles = table.ctypes.data_as(C.POINTER(C.c_void_p))
+        if arr.world.size > 1 and arr.memory == "device":
+            # the array's process map: lets the engine redistribute tiles that are not where SUMMA needs them
+            owners = np.fromiter((arr._owner(o) for o in range(tr.ntiles)), dtype=np.int32, count=tr.ntiles)
+            keep.append(owners)
+            d.owners = owners.ctypes.data_as(C.POINTER(C.c_int32))
         return d
 
     def eval(self) -> ContractionStats:
