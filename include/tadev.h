@@ -215,6 +215,12 @@ int tadev_plan_contraction(const char* target, const char* left, const char* rig
 int tadev_plan_contraction_opt(const char* target, const char* left, const char* right,
                                tadev_contraction_plan* out, int32_t* swapped);
 
+/* [host] GeneralPermutationOptimizer: plan of a general product (fused + contracted + free indices).
+ * *nfused = number of fused indices; 0 = not a general product (plan untouched). left_target /
+ * right_target / result_gemm receive the canonical index lists (fused..., external..., contracted...). */
+int tadev_plan_general_product(const char* target, const char* left, const char* right,
+                               tadev_contraction_plan* out, int32_t* nfused);
+
 /* ---- multi-GPU: communicators + SUMMA driver ------------------------------------------------
  * replaces detail::Summa (dist_eval/contraction_eval.h:55-2027) and its world.gop.bcast
  * row/column tile broadcasts (:712,:849,:903) by NCCL broadcasts of packed panels on

@@ -357,6 +357,54 @@ def test_general_products_dense(world, target, lidx, ridx):
     _check(world, target, lidx, ridx, trL, trR, trC, integer=False, factor=-0.75)
 
 
+def _patterned(world, tr, seed):
+    """make_patterned_array of tests/general_product.cpp:149-168: v = seed + sum_d 0.1^d * (x_d + 1)."""
+    idx = np.indices(tr.elements_shape).astype(np.float64)
+    full = np.full(tr.elements_shape, float(seed))
+    scale = 1.0
+    for d in range(tr.rank):
+        full = full + scale * (idx[d] + 1.0)
+        scale *= 0.1
+    return DistArray(world, tr).init_from_numpy(full), full
+
+
+def test_general_products_reference_cases(world):
+    """tests/general_product.cpp:183-294 on the device engine, same tilings and data pattern, against einsum:
+    batched GEMM, permuted arguments, batched outer product, fused broadcast on either side, non-canonical
+    target; plus the neighbouring pure contraction and pure Hadamard forms of the same arrays."""
+    a, A = _patterned(world, _tr((0, 2, 5), (0, 3, 4), (0, 2, 6, 7)), 1.0)      # b, i, j
+    b, B = _patterned(world, _tr((0, 2, 5), (0, 2, 6, 7), (0, 4, 5)), 2.0)      # b, j, k
+    c = DistArray(world, _tr((0, 2, 5), (0, 3, 4), (0, 4, 5)))
+    c["b,i,k"] = a["b,i,j"] * b["b,j,k"]
+    assert O.rel_frobenius(c.to_numpy(), np.einsum("bij,bjk->bik", A, B)) < TOL
+    d = DistArray(world, _tr((0, 3, 4), (0, 4, 5)))
+    d["i,k"] = a["b,i,j"] * b["b,j,k"]                                          # pure contraction
+    assert O.rel_frobenius(d.to_numpy(), np.einsum("bij,bjk->ik", A, B)) < TOL
+    e = DistArray(world, a.trange)
+    e["b,i,j"] = a["b,i,j"] * a["b,i,j"]                                        # pure Hadamard
+    assert O.rel_frobenius(e.to_numpy(), A * A) < TOL
+    a2, A2 = _patterned(world, _tr((0, 3, 4), (0, 2, 6, 7), (0, 2, 5)), 1.0)    # i, j, b
+    b2, B2 = _patterned(world, _tr((0, 4, 5), (0, 2, 6, 7), (0, 2, 5)), 2.0)    # k, j, b
+    c["b,i,k"] = a2["i,j,b"] * b2["k,j,b"]
+    assert O.rel_frobenius(c.to_numpy(), np.einsum("ijb,kjb->bik", A2, B2)) < TOL
+    a3, A3 = _patterned(world, _tr((0, 2, 5), (0, 3, 4)), 1.0)                  # b, i
+    b3, B3 = _patterned(world, _tr((0, 2, 5), (0, 4, 5)), 2.0)                  # b, k
+    c["b,i,k"] = a3["b,i"] * b3["b,k"]                                          # batched outer product
+    assert O.rel_frobenius(c.to_numpy(), np.einsum("bi,bk->bik", A3, B3)) < TOL
+    s1, S1 = _patterned(world, _tr((0, 2, 5)), 1.0)                             # b
+    cc = DistArray(world, b3.trange)
+    cc["b,k"] = s1["b"] * b3["b,k"]                                             # fused broadcast, left fully fused
+    assert O.rel_frobenius(cc.to_numpy(), S1[:, None] * B3) < TOL
+    cc["b,k"] = b3["b,k"] * s1["b"]                                             # ... and on the right
+    assert O.rel_frobenius(cc.to_numpy(), S1[:, None] * B3) < TOL
+    x, X = _patterned(world, _tr((0, 2, 4), (0, 3, 5)), 1.0)                    # orbital x auxiliary
+    w = DistArray(world, _tr((0, 2, 4), (0, 2, 4), (0, 3, 5)))
+    w["p,q,r1"] = x["p,r1"] * x["q,r1"]                                         # non-canonical target
+    assert O.rel_frobenius(w.to_numpy(), np.einsum("pr,qr->pqr", X, X)) < TOL
+    for t in (a, b, c, d, e, a2, b2, a3, b3, s1, cc, x, w):
+        t.release()
+
+
 def test_general_product_sparse_and_accumulate(world):
     """Block-sparse general product: result shape = SparseShape::gemm_batched (sparse_shape.h:1707-1900), i.e. the
     oracle's norm GEMM slab by slab, bit-exact; zero result tiles absent; c += accumulates."""

@@ -259,3 +259,50 @@ def test_summa_nccl_groups_agree_across_ranks(lib, grid, flags, density):
             for t in traces.values():
                 for cm, g, k, root, nb in t:
                     assert root == (k % Pc if cm == 0 else k % Pr) and nb > 0
+
+
+def test_general_product_planner_reference_known_answers(lib):
+    """tests/general_product.cpp:62-135 (GeneralPermutationOptimizer): fused / contracted / external classes,
+    canonical layouts (fused..., external..., contracted...) with the class order following the target, and the
+    two error cases (implicit reduction; pure Hadamard belongs to the element-wise engine)."""
+    def plan(target, left, right):
+        p, nf = _lib.ContractionPlanC(), C.c_int32(-1)
+        rc = lib.tadev_plan_general_product(target.encode(), left.encode(), right.encode(), C.byref(p), C.byref(nf))
+        return rc, p, nf.value
+
+    rc, p, nf = plan("c,b,i,k", "b,c,i,j", "c,j,b,k")  # two fused indices; class order follows the target
+    assert rc == 0 and nf == 2
+    assert (p.left_target, p.right_target, p.result_gemm) == (b"c,b,i,j", b"c,b,j,k", b"c,b,i,k")
+    assert p.perm_result[0] == -1 and list(p.perm_left[:4]) == [1, 0, 2, 3] and list(p.perm_right[:4]) == [0, 2, 1, 3]
+    assert p.inner_rank == 1 and (p.opA, p.opB) == (0, 0)
+    rc, p, nf = plan("i", "i,j", "i,j")  # Hadamard reduction: i fused, j contracted, no externals
+    assert rc == 0 and nf == 1 and (p.left_target, p.right_target, p.result_gemm) == (b"i,j", b"i,j", b"i")
+    assert p.perm_left[0] == -1 and p.perm_right[0] == -1 and p.perm_result[0] == -1 and p.inner_rank == 1
+    rc, p, nf = plan("b,i,k", "i,j,b", "k,j,b")  # non-canonical arguments are permuted
+    assert rc == 0 and nf == 1 and (p.left_target, p.right_target, p.result_gemm) == (b"b,i,j", b"b,j,k", b"b,i,k")
+    rc, p, nf = plan("p,q,r1", "p,r1", "q,r1")  # non-canonical target: evaluated as (r1,p,q), then permuted
+    assert rc == 0 and nf == 1 and p.result_gemm == b"r1,p,q" and list(p.perm_result[:3]) == [2, 0, 1]
+    rc, p, nf = plan("b,k", "b", "b,k")  # fused broadcast: the left argument is entirely fused
+    assert rc == 0 and nf == 1 and (p.left_target, p.right_target, p.result_gemm) == (b"b", b"b,k", b"b,k") and p.inner_rank == 0
+    assert plan("i,k", "b,i,j", "b,j,k")[2] == 0  # pure contraction: not a general product
+    assert plan("b,i", "b,i,j", "b,i")[0] == _lib.EINVAL  # implicit reduction over j is rejected
+    assert plan("b,i,j", "b,i,j", "b,i,j")[0] == _lib.EINVAL  # pure Hadamard: element-wise engine
+
+
+def test_operand_exchange_planner(lib):
+    """tadev_plan_contraction_opt: the exchanged product C^T = B^T A^T is chosen iff it needs fewer explicit
+    tile permutations (BASELINE config 4 becomes a plain NN product; config 5 stays as written)."""
+    def plan(target, left, right):
+        p, sw = _lib.ContractionPlanC(), C.c_int32(-1)
+        _lib.check(lib.tadev_plan_contraction_opt(target.encode(), left.encode(), right.encode(), C.byref(p), C.byref(sw)))
+        return p, sw.value
+
+    p, sw = plan("a,b,i,j", "c,d,i,j", "a,b,c,d")
+    assert sw == 1 and (p.opA, p.opB) == (0, 0) and p.perm_left[0] == p.perm_right[0] == p.perm_result[0] == -1
+    assert p.result_gemm == b"a,b,i,j"
+    p, sw = plan("i,a,j,b", "i,k,a,c", "j,c,k,b")
+    assert sw == 0 and p.perm_left[0] >= 0 and p.perm_right[0] >= 0 and p.perm_result[0] == -1
+    p, sw = plan("m,n", "m,k", "k,n")
+    assert sw == 0
+    p, sw = plan("n,m", "m,k", "k,n")
+    assert sw == 1 and (p.opA, p.opB) == (1, 1) and p.perm_result[0] == -1

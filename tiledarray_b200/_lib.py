@@ -156,6 +156,7 @@ PROTOTYPES = {
     "tadev_elementwise_info_get": (_i, [_vp, _P(ContractionInfoC)]),
     "tadev_elementwise_eval": (_i, [_vp, _vp, _P(_f)]),
     "tadev_elementwise_destroy": (_i, [_vp]),
+    "tadev_plan_general_product": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, _P(ContractionPlanC), _P(C.c_int32)]),
     "tadev_comm_unique_id": (_i, [_vp]),
     "tadev_comm_init": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "tadev_comm_destroy": (_i, [_vp]),

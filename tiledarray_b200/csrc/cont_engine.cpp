@@ -213,6 +213,64 @@ extern "C" int tadev_contract_options_default(tadev_contract_options* o) {
   return TADEV_OK;
 }
 
+// [host] GeneralPermutationOptimizer (expressions/permopt.h; tests/general_product.cpp:96-135): indices
+// present in both arguments AND in the target are fused (Hadamard / batch) indices. Canonical layouts:
+//   left (fused..., left external..., contracted...)   right (fused..., contracted..., right external...)
+//   result (fused..., left external..., right external...)
+// with the fused and external classes ordered as in the TARGET (so a target already laid out that way
+// needs no result permutation) and the contracted class as in the left argument. *nfused = 0 and an
+// untouched plan mean "not a general product" (pure contraction); a pure Hadamard product is an error
+// here (it belongs to the element-wise engine).
+extern "C" int tadev_plan_general_product(const char* target, const char* left, const char* right,
+                                          tadev_contraction_plan* out, int32_t* nfused) {
+  TADEV_REQUIRE(target && left && right && out && nfused, "tadev_plan_general_product: null");
+  *nfused = 0;
+  const auto T = split_idx(target), Li = split_idx(left), Ri = split_idx(right);
+  auto has = [](const std::vector<std::string>& v, const std::string& x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+  std::vector<std::string> Hh, oL, Kk, oR;
+  for (auto& x : T) if (has(Li, x) && has(Ri, x)) Hh.push_back(x);
+  if (Hh.empty()) return TADEV_OK;
+  for (auto& x : T) { if (has(Li, x) && !has(Ri, x)) oL.push_back(x); if (has(Ri, x) && !has(Li, x)) oR.push_back(x); }
+  for (auto& x : Li) if (has(Ri, x) && !has(T, x)) Kk.push_back(x);
+  TADEV_REQUIRE(!(Kk.empty() && oL.empty() && oR.empty()), "a pure Hadamard product is evaluated by the element-wise engine (tadev_elementwise_create)");
+  TADEV_REQUIRE(Li.size() <= 16 && Ri.size() <= 16 && T.size() <= 16, "general product: rank > 16");
+  // every index of an argument must be fused, contracted or kept: no implicit reductions
+  for (auto& x : Li) TADEV_REQUIRE(has(Ri, x) || has(T, x), "general product: left index '%s' appears in neither the right argument nor the target", x.c_str());
+  for (auto& x : Ri) TADEV_REQUIRE(has(Li, x) || has(T, x), "general product: right index '%s' appears in neither the left argument nor the target", x.c_str());
+  for (size_t i = 0; i < T.size(); ++i) {
+    TADEV_REQUIRE(has(Li, T[i]) || has(Ri, T[i]), "general product: target index '%s' is in neither argument", T[i].c_str());
+    for (size_t j = 0; j < i; ++j) TADEV_REQUIRE(T[i] != T[j], "general product: repeated target index '%s'", T[i].c_str());
+  }
+  std::vector<std::string> cL = Hh, cR = Hh, cRes = Hh;
+  cL.insert(cL.end(), oL.begin(), oL.end()); cL.insert(cL.end(), Kk.begin(), Kk.end());
+  cR.insert(cR.end(), Kk.begin(), Kk.end()); cR.insert(cR.end(), oR.begin(), oR.end());
+  cRes.insert(cRes.end(), oL.begin(), oL.end()); cRes.insert(cRes.end(), oR.begin(), oR.end());
+  TADEV_REQUIRE(cL.size() == Li.size() && cR.size() == Ri.size() && cRes.size() == T.size(), "general product: repeated index in an argument");
+  tadev_contraction_plan G;
+  memset(&G, 0, sizeof(G));
+  G.left_rank = (int32_t)Li.size(); G.right_rank = (int32_t)Ri.size(); G.result_rank = (int32_t)cRes.size();
+  G.inner_rank = (int32_t)Kk.size(); G.opA = G.opB = TADEV_OP_N; G.left_permtype = G.right_permtype = 1;
+  for (int i = 0; i < 16; ++i) G.perm_left[i] = G.perm_right[i] = G.perm_result[i] = -1;
+  auto image = [](const std::vector<std::string>& from, const std::vector<std::string>& to, int32_t* perm) {
+    bool ident = true;
+    for (size_t i = 0; i < from.size(); ++i) ident = ident && from[i] == to[i];
+    if (ident) return;
+    for (size_t i = 0; i < from.size(); ++i) perm[i] = (int32_t)(std::find(to.begin(), to.end(), from[i]) - to.begin());
+  };
+  image(Li, cL, G.perm_left); image(Ri, cR, G.perm_right); image(cRes, T, G.perm_result);
+  if (G.perm_left[0] >= 0) G.left_permtype = 3;
+  if (G.perm_right[0] >= 0) G.right_permtype = 3;
+  auto join = [](const std::vector<std::string>& v, char* dst, size_t cap) {
+    std::string j;
+    for (size_t i = 0; i < v.size(); ++i) { if (i) j += ","; j += v[i]; }
+    snprintf(dst, cap, "%s", j.c_str());
+  };
+  join(cL, G.left_target, sizeof(G.left_target)); join(cR, G.right_target, sizeof(G.right_target)); join(cRes, G.result_gemm, sizeof(G.result_gemm));
+  *out = G;
+  *nfused = (int32_t)Hh.size();
+  return TADEV_OK;
+}
+
 extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, const char* left_idx, const char* right_idx,
                                         const tadev_array_desc* left, const tadev_array_desc* right, double factor,
                                         const tadev_contract_options* options, tadev_contraction** out) {
@@ -223,43 +281,11 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
   if (options) E->opt = *options; else tadev_contract_options_default(&E->opt);
   int rc;
   {
-    // fused (Hadamard / batch) indices: present in both arguments AND kept in the target => general product
-    // (TensorProduct::General, expressions/cont_engine.h:679-1100, tile_op/batched_contract_reduce.h).
-    // Canonical layouts, as the reference's GeneralPermutationOptimizer produces them:
-    //   left (fused..., left outer..., contracted...)   right (fused..., contracted..., right outer...)
-    //   result (fused..., left outer..., right outer...);  anything else is permuted explicitly.
-    const auto T = split_idx(target), Li = split_idx(left_idx), Ri = split_idx(right_idx);
-    auto has = [](const std::vector<std::string>& v, const std::string& x) { return std::find(v.begin(), v.end(), x) != v.end(); };
-    std::vector<std::string> Hh, oL, Kk, oR;
-    for (auto& x : Li) { if (has(Ri, x)) { if (has(T, x)) Hh.push_back(x); else Kk.push_back(x); } else oL.push_back(x); }
-    for (auto& x : Ri) if (!has(Li, x)) oR.push_back(x);
-    if (!Hh.empty()) {
-      TADEV_REQUIRE(!(Kk.empty() && oL.empty() && oR.empty()), "a pure Hadamard product is evaluated by the element-wise engine (tadev_elementwise_create)");
-      TADEV_REQUIRE(Li.size() <= 16 && Ri.size() <= 16 && T.size() <= 16, "general product: rank > 16");
-      std::vector<std::string> cL = Hh, cR = Hh, cRes = Hh;
-      cL.insert(cL.end(), oL.begin(), oL.end()); cL.insert(cL.end(), Kk.begin(), Kk.end());
-      cR.insert(cR.end(), Kk.begin(), Kk.end()); cR.insert(cR.end(), oR.begin(), oR.end());
-      cRes.insert(cRes.end(), oL.begin(), oL.end()); cRes.insert(cRes.end(), oR.begin(), oR.end());
-      TADEV_REQUIRE(T.size() == cRes.size(), "general product: target rank %zu != result rank %zu", T.size(), cRes.size());
-      for (auto& x : cRes) TADEV_REQUIRE(has(T, x), "general product: result index '%s' is not in the target", x.c_str());
-      tadev_contraction_plan& G = E->plan;
-      memset(&G, 0, sizeof(G));
-      G.left_rank = (int32_t)Li.size(); G.right_rank = (int32_t)Ri.size(); G.result_rank = (int32_t)cRes.size();
-      G.inner_rank = (int32_t)Kk.size(); G.opA = G.opB = TADEV_OP_N; G.left_permtype = G.right_permtype = 1;
-      for (int i = 0; i < 16; ++i) G.perm_left[i] = G.perm_right[i] = G.perm_result[i] = -1;
-      auto image = [](const std::vector<std::string>& from, const std::vector<std::string>& to, int32_t* perm) {
-        bool ident = true;
-        for (size_t i = 0; i < from.size(); ++i) ident = ident && from[i] == to[i];
-        if (ident) return;
-        for (size_t i = 0; i < from.size(); ++i) perm[i] = (int32_t)(std::find(to.begin(), to.end(), from[i]) - to.begin());
-      };
-      image(Li, cL, G.perm_left); image(Ri, cR, G.perm_right); image(cRes, T, G.perm_result);
-      if (G.perm_left[0] >= 0) G.left_permtype = 3;
-      if (G.perm_right[0] >= 0) G.right_permtype = 3;
-      E->general = true;
-      E->nh = (int)Hh.size();
-      rc = TADEV_OK;
-    } else if (E->opt.exchange_operands) rc = tadev_plan_contraction_opt(target, left_idx, right_idx, &E->plan, &E->swapped);
+    int32_t nfused = 0;
+    rc = tadev_plan_general_product(target, left_idx, right_idx, &E->plan, &nfused);
+    if (rc) return rc;
+    if (nfused > 0) { E->general = true; E->nh = nfused; }
+    else if (E->opt.exchange_operands) rc = tadev_plan_contraction_opt(target, left_idx, right_idx, &E->plan, &E->swapped);
     else rc = tadev_plan_contraction(target, left_idx, right_idx, &E->plan);
   }
   if (rc) return rc;
