@@ -47,9 +47,16 @@ class TiledRange1 {
   TiledRange1(std::initializer_list<int64_t> bounds) : b_(bounds) { check_(); }
   template <typename It>
   TiledRange1(It first, It last) : b_(first, last) { check_(); }
+  // make_uniform (tiled_range1.h:289-313): ceil(extent / tile) tiles, as uniform as possible (the first tiles
+  // are one element larger), e.g. make_uniform(55, 10) == {0,10,19,28,37,46,55}
   static TiledRange1 make_uniform(int64_t extent, int64_t tile, int64_t lo = 0) {
+    TA_TADEV_ASSERT(extent > 0 && tile > 0, "TiledRange1::make_uniform: positive extent and tile size required");
+    const int64_t ntiles = (extent + tile - 1) / tile;
+    const int64_t quot = (extent + ntiles - 1) / ntiles, rem = (extent + ntiles - 1) % ntiles;
+    const int64_t avg = quot - 1, nplus = rem + 1;
     std::vector<int64_t> b;
-    for (int64_t x = lo; x < lo + extent; x += tile) b.push_back(x);
+    int64_t e = lo;
+    for (int64_t i = 0; i < ntiles; ++i) { b.push_back(e); e += i < nplus ? avg + 1 : avg; }
     b.push_back(lo + extent);
     return TiledRange1(b.begin(), b.end());
   }

@@ -75,7 +75,16 @@ class TiledRange1:
 
     @staticmethod
     def uniform(extent: int, tile: int, lo: int = 0) -> "TiledRange1":
-        b = list(range(lo, lo + extent, tile)) + [lo + extent]
+        """TiledRange1::make_uniform (tiled_range1.h:289-313): ceil(extent/tile) tiles, the first
+        (extent + ntiles - 1) % ntiles + 1 of them one element larger than the rest."""
+        ntiles = (extent + tile - 1) // tile
+        quot, rem = divmod(extent + ntiles - 1, ntiles)
+        avg, nplus = quot - 1, rem + 1
+        b, e = [], lo
+        for i in range(ntiles):
+            b.append(e)
+            e += avg + 1 if i < nplus else avg
+        b.append(lo + extent)
         return TiledRange1(tuple(b))
 
     @property

@@ -34,6 +34,15 @@ world.init_comm(1, 1)
 peak = max(dev.probe_fp64_peak(0, 40000)[0] for _ in range(2))
 
 
+def example_tiling(range_size, tile):
+    """make_uniform_tiling of examples/gemm/ta_cc_abcd.cpp:56-65: tile-size steps, the last tile takes the remainder
+    (v=800, tile=64 -> 12 x 64 + 32; NOT TiledRange1::make_uniform, which would give 7 x 62 + 6 x 61)."""
+    b = list(range(0, range_size + 1, tile))
+    if b[-1] != range_size:
+        b.append(range_size)
+    return TiledRange1(*b)
+
+
 def host_tile(arr, ordinal, seed):
     ext = arr.trange.tile_extent(arr.trange.tile_index(ordinal))
     return util_rng.tile_fill(ordinal, int(np.prod(ext)), seed).reshape(ext)
@@ -141,8 +150,8 @@ if "C3" in which:
         x.release()
 
 if "C4r" in which:
-    o1 = TiledRange1(0, 64, 100)
-    v1 = TiledRange1.make_uniform(256, 64)
+    o1 = example_tiling(100, 64)
+    v1 = example_tiling(256, 64)
     T2 = DistArray(world, TiledRange([v1, v1, o1, o1])).fill_random(7)
     V = DistArray(world, TiledRange([v1, v1, v1, v1])).fill_random(8)
     R = DistArray(world, TiledRange([v1, v1, o1, o1]))
@@ -152,8 +161,8 @@ if "C4r" in which:
         x.release()
 
 if "C4" in which:
-    o1 = TiledRange1(0, 64, 100)
-    v1 = TiledRange1.make_uniform(800, 64)
+    o1 = example_tiling(100, 64)
+    v1 = example_tiling(800, 64)
     T2 = DistArray(world, TiledRange([v1, v1, o1, o1])).fill_random(7)
     V = DistArray(world, TiledRange([v1, v1, v1, v1]), memory="lazy", lazy_seed=8)
     R = DistArray(world, TiledRange([v1, v1, o1, o1]))

@@ -306,3 +306,30 @@ def test_operand_exchange_planner(lib):
     assert sw == 0
     p, sw = plan("n,m", "m,k", "k,n")
     assert sw == 1 and (p.opA, p.opB) == (1, 1) and p.perm_result[0] == -1
+
+
+def test_make_uniform_reference_known_answers():
+    """tests/tiled_range1.cpp:352-393 (TiledRange1::make_uniform) on the Python front-end and on the oracle."""
+    from tiledarray_b200.tiledarray import TiledRange1
+    cases = [((3, 10, 0), (0, 3)), ((50, 10, 0), (0, 10, 20, 30, 40, 50)), ((55, 10, 0), (0, 10, 19, 28, 37, 46, 55)),
+             ((59, 10, 0), (0, 10, 20, 30, 40, 50, 59)), ((3, 10, 3), (3, 6)), ((50, 10, 10), (10, 20, 30, 40, 50, 60)),
+             ((55, 10, 10), (10, 20, 29, 38, 47, 56, 65)), ((59, 10, 10), (10, 20, 30, 40, 50, 60, 69)),
+             ((50, 30, 0), (0, 25, 50))]
+    for (extent, tile, lo), want in cases:
+        assert TiledRange1.make_uniform(extent, tile, lo).bounds == want
+        assert O.TiledRange1.uniform(extent, tile, lo).bounds == want
+    assert TiledRange1.make_uniform(32768, 1024).extents == [1024] * 32  # the benchmark tilings are unaffected
+
+
+def test_cpp_host_api(lib):
+    """include/tiledarray.hpp metadata classes + host-only planners, in C++, without a GPU
+    (tests/cpp/test_host_api.cpp restates tests/tiled_range1.cpp, tiled_range.cpp, general_product.cpp:96-135)."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "test_host_api")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "tiledarray_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and "HOST API TESTS PASSED" in out.stdout, out.stdout + out.stderr

@@ -50,7 +50,18 @@ class TiledRange1:
 
     @staticmethod
     def make_uniform(extent: int, tile: int, lo: int = 0) -> "TiledRange1":
-        return TiledRange1(*(list(range(lo, lo + extent, tile)) + [lo + extent]))
+        """TiledRange1::make_uniform (tiled_range1.h:289-313): ceil(extent / tile) tiles, as uniform as possible
+        (the first tiles are one element larger), e.g. make_uniform(55, 10) == {0,10,19,28,37,46,55}."""
+        _ta_assert(extent > 0 and tile > 0, "TiledRange1::make_uniform: positive extent and tile size required")
+        ntiles = (extent + tile - 1) // tile
+        quot, rem = divmod(extent + ntiles - 1, ntiles)
+        avg, nplus = quot - 1, rem + 1
+        bounds, e = [], lo
+        for i in range(ntiles):
+            bounds.append(e)
+            e += avg + 1 if i < nplus else avg
+        bounds.append(lo + extent)
+        return TiledRange1(*bounds)
 
     @property
     def ntiles(self) -> int:
