@@ -235,6 +235,9 @@ int tadev_comm_destroy(tadev_ctx* ctx);
 int tadev_exchange_tiles(tadev_ctx* ctx, tadev_stream s, int nsend, const void* const* h_src, const size_t* h_sbytes,
                          const int32_t* h_dst_rank, int nrecv, void* const* h_dst, const size_t* h_rbytes,
                          const int32_t* h_src_rank);
+/* Shape replication: element-wise max of a device norm array over all ranks (the SparseShape constructor's
+ * world.gop.max, sparse_shape.h:416); every rank passes the norms of its own tiles and zeros elsewhere. */
+int tadev_shape_allreduce_max_f32(tadev_ctx* ctx, tadev_stream s, float* d_norms, int64_t n);
 /* which=0: row communicator (A panels), which=1: column communicator (B panels). */
 int tadev_bcast_panel(tadev_ctx* ctx, tadev_stream s, int which, int root, void* d_buf, size_t bytes);
 
@@ -314,6 +317,8 @@ typedef struct {
   int64_t h2d_bytes;  /* host->device bytes moved inside the call (host-resident operands) */
   int64_t d2h_bytes;  /* device->host bytes moved inside the call (host-resident result) */
   int64_t lazy_tiles; /* tiles materialised by providers */
+  float gemm_ms;      /* sum of the grouped-GEMM launches' own durations (CUDA events around each launch) */
+  float list_ms;      /* sum of the device tile-list builder launches' durations */
 } tadev_summa_stats;
 
 int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_stats* stats);
@@ -353,6 +358,12 @@ typedef struct {
   int64_t stream_permute_bytes; /* auto: stream when the permuted copy would exceed this size */
   int32_t depth, steps_per_launch, row_blocks; /* forwarded to the SUMMA plan (0 = auto) */
   float threshold;              /* SparseShape threshold */
+  /* optional result mask: `(a("m,k") * b("k,n")).set_shape(mask)` (expressions/expr.h:116, applied after
+   * make_shape by SparseShape::mask, cont_engine.h:526-528, sparse_shape.h:653-676; the reference's own
+   * block-sparse example uses it, examples/gemm/ta_sparse.cpp:190). Scaled norms over the TARGET tile grid
+   * (host, row-major), read during tadev_contraction_create only; NULL = none. */
+  const float* mask_norms;
+  float mask_threshold;
 } tadev_contract_options;
 int tadev_contract_options_default(tadev_contract_options* o);
 
@@ -376,6 +387,21 @@ typedef struct {
   float permute_ms;               /* up-front argument permutations + result permutation */
 } tadev_contract_stats;
 
+/* [host] the distribution SUMMA wants for the operands of an expression (no device, no tile tables needed):
+ * the ProcGrid for `nranks` ranks and, per tile of each operand (original tiling, row-major ordinal), its
+ * position (frow, fcol) in the fused GEMM-side tile grid; owner = (frow % Pr) * Pc + fcol % Pc
+ * (proc_grid.h:566-597). *_role: 0 = the operand is the GEMM's left operand A(i,k), 1 = right B(k,j) (after
+ * the optional operand exchange). Arrays created with these maps are contracted without redistribution, and
+ * an arena ordered by (fcol, frow) [role 0] / (frow, fcol) [role 1] makes SUMMA panels contiguous. */
+typedef struct {
+  int32_t swapped, Pr, Pc, Mt, Nt, Kt, opA, opB, left_role, right_role;
+} tadev_contraction_layout_info;
+int tadev_contraction_layout(const char* target, const char* left_idx, const char* right_idx,
+                             const tadev_array_desc* left, const tadev_array_desc* right,
+                             const tadev_contract_options* options /* NULL = defaults */, int nranks,
+                             tadev_contraction_layout_info* info, int32_t* left_frow, int32_t* left_fcol,
+                             int32_t* right_frow, int32_t* right_fcol);
+
 int tadev_contraction_create(tadev_ctx* ctx, const char* target, const char* left_idx, const char* right_idx,
                              const tadev_array_desc* left, const tadev_array_desc* right, double factor,
                              const tadev_contract_options* options /* NULL = defaults */, tadev_contraction** out);
@@ -385,6 +411,11 @@ int tadev_contraction_owner(const tadev_contraction* c, int64_t target_ordinal, 
  * accumulate != 0: C += (the arena holds the previous result with the same layout). */
 int tadev_contraction_eval(tadev_contraction* c, void* result_arena, int result_memory, int accumulate,
                            tadev_contract_stats* stats);
+/* Same, into caller-owned tiles: result_tiles[t] = storage of local result tile t (info.ordinals[t]). This is
+ * the entry `c("m,n") += a("m,k") * b("k,n")` uses: the existing array's own tile pointers, whatever its
+ * arena layout (a result permutation, if any, is applied to the product before it is added). */
+int tadev_contraction_eval_tiles(tadev_contraction* c, void* const* result_tiles, int result_memory, int accumulate,
+                                 tadev_contract_stats* stats);
 int tadev_contraction_destroy(tadev_contraction* c);
 
 /* ---- the element-wise engine -----------------------------------------------

@@ -487,3 +487,147 @@ def test_cont_host_resident_arrays(world, where, sparse):
         ContEngine.steps_per_launch, ContEngine.row_blocks = old
     for x in (a, b, c):
         x.release()
+
+
+def _otr(*dims):
+    return O.TiledRange(tuple(O.TiledRange1(d.bounds) for d in dims))
+
+
+@pytest.mark.parametrize("permuted", [False, True])
+def test_cont_set_shape_mask(world, permuted):
+    """c("m,n") = (a("m,k") * b("k,n")).set_shape(mask) — the reference's own block-sparse example expression
+    (examples/gemm/ta_sparse.cpp:190; ContEngine::init_struct applies SparseShape::mask after make_shape,
+    cont_engine.h:526-528, sparse_shape.h:653-676). Result shape bit-exact vs the oracle's gemm(...).mask(...),
+    masked tiles absent, values exact, and only pairs that feed surviving result tiles are executed."""
+    rng = np.random.default_rng(77)
+    dm, dk, dn = _uniform(40, 8), _uniform(48, 8), _uniform(56, 8)
+    trL, trR = _tr(dm, dk), _tr(dk, dn)
+    (a, A, nA), (b, B, nB) = _sparse_pair(world, trL, trR, 0.6, rng)
+    trC = _tr(dn, dm) if permuted else _tr(dm, dn)
+    mnorms = np.where(rng.random(trC.tiles_shape) < 0.5, np.float32(3.0), np.float32(0.0)).astype(np.float32)
+    mask = SparseShape(world, mnorms, trC)
+    c = DistArray(world, trC)
+    if permuted:
+        c["n,m"] = (a["m,k"] * b["k,n"]).set_shape(mask)
+    else:
+        c["m,n"] = (a["m,k"] * b["k,n"]).set_shape(mask)
+    oa = O.SparseShape.from_tile_norms(nA, _otr(dm, dk))
+    ob = O.SparseShape.from_tile_norms(nB, _otr(dk, dn))
+    om = O.SparseShape.from_tile_norms(mnorms, _otr(dn, dm) if permuted else _otr(dm, dn))
+    oc = oa.gemm(ob, 1.0, O.GemmHelper(0, 0, 2, 2, 2), perm=[1, 0] if permuted else None).mask(om)
+    assert np.array_equal(c.shape.norms.view(np.uint32), oc.norms.view(np.uint32))
+    assert c.shape.zero_tile_count == oc.zero_tile_count
+    ref = (A @ B).T if permuted else A @ B
+    keep = np.zeros_like(ref)
+    for o in range(trC.ntiles):
+        sl = trC.tile_slices(trC.tile_index(o))
+        if oc.is_zero(o):
+            assert o not in c.tiles
+        else:
+            keep[sl] = ref[sl]
+    assert np.array_equal(c.to_numpy(), keep)
+    nzc = (oc.norms >= np.float32(oc.threshold))
+    nzc = nzc.T if permuted else nzc
+    pa, pb = (oa.norms >= np.float32(oa.threshold)).astype(int), (ob.norms >= np.float32(ob.threshold)).astype(int)
+    assert ContEngine.last_stats.npairs == int(((pa @ pb) * nzc).sum())
+    for x in (a, b, c):
+        x.release()
+    # dense policy has no shape override
+    t = _uniform(16, 8)
+    da, _ = _dense_array(world, _tr(t, t), rng)
+    with pytest.raises(TiledArrayException):
+        DistArray(world, _tr(t, t))["m,n"] = (da["m,k"] * da["k,n"]).set_shape(SparseShape(world, np.ones((2, 2), np.float32), _tr(t, t)))
+    da.release()
+
+
+def test_cont_accumulate_into_foreign_layouts(world):
+    """c += a*b must use the EXISTING array's own tile pointers: arrays whose arena order differs from the engine's
+    layout, results of an earlier product with a result permutation, sparse results with a superset shape, products
+    that need a result permutation, and products with tiles c does not have yet (shape union)."""
+    rng = np.random.default_rng(11)
+    t = TiledRange1(0, 8, 20, 32)
+    tr = _tr(t, t)
+    a, A = _dense_array(world, tr, rng, True)
+    b, B = _dense_array(world, tr, rng, True)
+    # (a) c created with a reversed arena order
+    c0full = KA.int_tile(rng, tr.elements_shape)
+    c = DistArray(world, tr, arena_order=list(range(tr.ntiles))[::-1]).init_from_numpy(c0full)
+    c["m,n"] += a["m,k"] * b["k,n"]
+    assert np.array_equal(c.to_numpy(), c0full + A @ B)
+    # (b) c produced by a product that needed a result permutation (its offsets follow the GEMM key order)
+    u = TiledRange1(0, 6, 16)
+    x, X = _dense_array(world, _tr(t, u), rng, True)
+    y, Y = _dense_array(world, _tr(u, t), rng, True)
+    d = DistArray(world, _tr(t, t))
+    ContEngine.exchange_operands = False
+    try:
+        d["n,m"] = x["m,k"] * y["k,n"]
+        assert ContEngine.last_stats.swapped is False
+        d["m,n"] += a["m,k"] * b["k,n"]                      # plain product into the permuted-layout array
+        assert np.array_equal(d.to_numpy(), (X @ Y).T + A @ B)
+        d["n,m"] += x["m,k"] * y["k,n"]                      # (d) += of a product that needs a result permutation
+        assert np.array_equal(d.to_numpy(), 2 * (X @ Y).T + A @ B)
+    finally:
+        ContEngine.exchange_operands = True
+    # (c) sparse c with a superset shape, then (e) a product with tiles c lacks (union)
+    (sa, SA, nA), (sb, SB, nB) = _sparse_pair(world, tr, tr, 0.4, rng)
+    full = KA.int_tile(rng, tr.elements_shape)
+    sup = DistArray(world, tr, SparseShape(world, np.full(tr.tiles_shape, 50.0, np.float32), tr)).init_from_numpy(full)
+    sup["m,n"] += sa["m,k"] * sb["k,n"]
+    assert np.array_equal(sup.to_numpy(), full + SA @ SB)
+    few = np.zeros(tr.tiles_shape, np.float32)
+    few[0, 0] = 40.0
+    sub_full = np.zeros(tr.elements_shape)
+    sub_full[tr.tile_slices((0, 0))] = KA.int_tile(rng, tr.tile_extent((0, 0)))
+    sub = DistArray(world, tr, SparseShape(world, few, tr)).init_from_numpy(sub_full)
+    sub["m,n"] += sa["m,k"] * sb["k,n"]
+    assert np.array_equal(sub.to_numpy(), sub_full + SA @ SB)
+    prod_nz = ((nA > 0).astype(int) @ (nB > 0).astype(int)) > 0
+    for o in range(tr.ntiles):
+        i, j = tr.tile_index(o)
+        assert (o in sub.tiles) == bool(prod_nz[i, j] or (i, j) == (0, 0))
+        assert sub.is_zero(o) == (o not in sub.tiles)
+    for z in (a, b, c, x, y, d, sa, sb, sup, sub):
+        z.release()
+
+
+def test_c3_shaped_every_tile(world):
+    """BASELINE config 3's structure at a reduced tile size: 128 x 128 tile grid, 10 % random tile density, tile 8
+    (N = 1024). EVERY result tile is compared with the oracle (dense numpy product of the block-sparse operands),
+    the result shape with the oracle's SparseShape::gemm bit for bit, and the executed tile-pair count with the
+    tile lists (ta_sparse.cpp:193 flop convention)."""
+    nt, T = 128, 8
+    t = _uniform(nt * T, T)
+    tr = _tr(t, t)
+    rng = np.random.default_rng(3)
+
+    def make(seed):
+        r = np.random.default_rng(seed)
+        nz = r.permutation(nt * nt)[: int(0.10 * nt * nt)]
+        full = np.zeros((nt * T, nt * T))
+        norms = np.zeros((nt, nt), np.float32)
+        for o in nz:
+            i, j = divmod(int(o), nt)
+            blk = KA.int_tile(rng, (T, T))
+            full[i * T:(i + 1) * T, j * T:(j + 1) * T] = blk
+            norms[i, j] = np.float32(np.linalg.norm(blk))
+        return DistArray(world, tr, SparseShape(world, norms, tr)).init_from_numpy(full), full, norms
+
+    a, A, nA = make(5)
+    b, B, nB = make(6)
+    c = DistArray(world, tr)
+    c["m,n"] = a["m,k"] * b["k,n"]
+    otr = _otr(t, t)
+    oa, ob = O.SparseShape.from_tile_norms(nA, otr), O.SparseShape.from_tile_norms(nB, otr)
+    oc = oa.gemm(ob, 1.0, O.GemmHelper(0, 0, 2, 2, 2))
+    assert np.array_equal(c.shape.norms.view(np.uint32), oc.norms.view(np.uint32))
+    ref = A @ B
+    got = c.to_numpy()
+    assert np.array_equal(got, ref)  # every tile (absent tiles are zero blocks of to_numpy)
+    nz_tiles = int((oc.norms >= np.float32(oc.threshold)).sum())
+    assert len(c.tiles) == nz_tiles
+    pairs = int((((oa.norms >= np.float32(oa.threshold)).astype(int)) @ ((ob.norms >= np.float32(ob.threshold)).astype(int))).sum())
+    assert ContEngine.last_stats.npairs == pairs
+    assert ContEngine.last_stats.flops == 2.0 * pairs * T ** 3
+    for x in (a, b, c):
+        x.release()

@@ -95,6 +95,41 @@ def test_grouped_gemm_chained_accumulation(dev, even):
         b.free()
 
 
+@pytest.mark.parametrize("tile", [1024, 512])
+@pytest.mark.parametrize("opA", [OP_N, OP_T])
+@pytest.mark.parametrize("opB", [OP_N, OP_T])
+def test_ws_kernel_random_baseline_tiles(dev, tile, opA, opB):
+    """The warp-specialised TMA kernel on RANDOM data at BASELINE's tile sizes (1024^3: configs 2 and 5; 512^3:
+    config 3), all four op combinations, a chain of three tile pairs per result tile (ContractReduce over K) with
+    beta = 0 and beta = 1 groups in one launch, against the oracle's vendor DGEMM, tile by tile, <= 1e-12 rel.
+    Frobenius. (Linearity / fill(1) properties cannot see a consistent index error; random data does.)"""
+    rng = np.random.default_rng(tile + 2 * opA + opB)
+    m = n = k = tile
+    nchain = 3
+    groups, refs, bufs = [], [], []
+    for gi in range(2):
+        As = [rng.uniform(-1, 1, (m, k) if opA == OP_N else (k, m)) for _ in range(nchain)]
+        Bs = [rng.uniform(-1, 1, (k, n) if opB == OP_N else (n, k)) for _ in range(nchain)]
+        C0 = rng.uniform(-1, 1, (m, n))
+        dAs, dBs, dC = [dev.upload(a) for a in As], [dev.upload(b) for b in Bs], dev.upload(C0)
+        bufs += dAs + dBs + [dC]
+        groups.append((dC.ptr, m, n, gi, [(a.ptr, b.ptr, k) for a, b in zip(dAs, dBs)]))
+        ref = C0.copy() if gi else np.zeros((m, n))
+        for a, b in zip(As, Bs):
+            ref = ocpu.gemm(opA, opB, m, n, k, 0.75, a, b, 1.0, ref)
+        refs.append((dC, ref))
+    dev.gemm_grouped(opA, opB, 0.75, groups)
+    for dC, ref in refs:
+        got = dev.download(dC, np.float64, (m, n))
+        assert O.rel_frobenius(got, ref) < TOL
+        # block by block: a misplaced 128 x 128 block must not hide in the global norm
+        for bi in range(0, m, 128):
+            for bj in range(0, n, 128):
+                assert O.rel_frobenius(got[bi:bi + 128, bj:bj + 128], ref[bi:bi + 128, bj:bj + 128]) < 1e-11
+    for b in bufs:
+        b.free()
+
+
 def test_gemm_argument_errors(dev):
     """Error behaviour of the boundary: bad arguments return TADEV_EINVAL (TA_ASSERT analogue)."""
     d = dev.alloc(64)

@@ -170,7 +170,8 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
                "tadev_contraction_info": L.ContractionInfoC, "tadev_contract_stats": L.ContractStatsC,
                "tadev_summa_plan": L.SummaPlanC, "tadev_summa_stats": L.SummaStatsC, "tadev_permute_source": L.PermuteSourceC,
                "tadev_uniform_source": L.UniformSourceC, "tadev_gemm_group": L.GemmGroup, "tadev_gemm_task": L.GemmTask,
-               "tadev_proc_grid": L.ProcGridC, "tadev_contraction_plan": L.ContractionPlanC}
+               "tadev_proc_grid": L.ProcGridC, "tadev_contraction_plan": L.ContractionPlanC,
+               "tadev_contraction_layout_info": L.LayoutInfoC}
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "tadev.h"', "int main(void){"]
     for cname, py in structs.items():
         lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
@@ -333,3 +334,61 @@ def test_cpp_host_api(lib):
     env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "tiledarray_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and "HOST API TESTS PASSED" in out.stdout, out.stdout + out.stderr
+
+
+def test_contraction_layout_named_configs():
+    """tadev_contraction_layout: where SUMMA wants every operand tile (fused GEMM-side position, ProcGrid) for the
+    BASELINE expressions: plain matrix product, config 4 (operands exchanged: R[ab,ij] = V[ab,cd] T[cd,ij]) and
+    config 5 (both operands explicitly permuted: A -> (i,a | c,k), B -> (c,k | j,b))."""
+    from tiledarray_b200.tiledarray import TiledRange, TiledRange1, contraction_layout
+    t = TiledRange1.make_uniform(40, 10)
+    u = TiledRange1.make_uniform(30, 10)
+    tr_mk, tr_kn = TiledRange([t, u]), TiledRange([u, t])
+    info, (lr, lc), (rr, rc) = contraction_layout(8, "m,n", "m,k", tr_mk, "k,n", tr_kn)
+    assert (info.swapped, info.Mt, info.Nt, info.Kt, info.left_role, info.right_role) == (0, 4, 4, 3, 0, 1)
+    assert (info.Pr, info.Pc) == (4, 2)
+    for o in range(tr_mk.ntiles):
+        assert (lr[o], lc[o]) == divmod(o, 3)
+    for o in range(tr_kn.ntiles):
+        assert (rr[o], rc[o]) == divmod(o, 4)
+    # config 4 miniature: o tiles (2), v tiles (3)
+    o1, v1 = TiledRange1(0, 4, 6), TiledRange1(0, 3, 6, 8)
+    trT, trV = TiledRange([v1, v1, o1, o1]), TiledRange([v1, v1, v1, v1])
+    info, (lr, lc), (rr, rc) = contraction_layout(8, "a,b,i,j", "c,d,i,j", trT, "a,b,c,d", trV)
+    assert info.swapped == 1 and (info.opA, info.opB) == (0, 0) and (info.left_role, info.right_role) == (1, 0)
+    assert (info.Mt, info.Nt, info.Kt) == (9, 4, 9)
+    for o in range(trT.ntiles):  # T(c,d,i,j) is the GEMM's right operand B(k = cd, j = ij)
+        c, d, i, j = trT.tile_index(o)
+        assert (lr[o], lc[o]) == (c * 3 + d, i * 2 + j)
+    for o in range(trV.ntiles):  # V(a,b,c,d) is the GEMM's left operand A(i = ab, k = cd)
+        a, b, c, d = trV.tile_index(o)
+        assert (rr[o], rc[o]) == (a * 3 + b, c * 3 + d)
+    # without the exchange: as written, T is the left operand with opA = T (stored [k][m])
+    info2, (lr2, lc2), _ = contraction_layout(8, "a,b,i,j", "c,d,i,j", trT, "a,b,c,d", trV, exchange_operands=False)
+    assert info2.swapped == 0 and (info2.opA, info2.opB) == (1, 1) and info2.left_role == 0
+    for o in range(trT.ntiles):
+        c, d, i, j = trT.tile_index(o)
+        assert (lr2[o], lc2[o]) == (i * 2 + j, c * 3 + d)
+    # config 5 miniature
+    s1, b1 = TiledRange1(0, 2, 4), TiledRange1(0, 3, 6, 9)
+    trA, trB = TiledRange([s1, s1, b1, b1]), TiledRange([s1, b1, s1, b1])
+    info, (lr, lc), (rr, rc) = contraction_layout(4, "i,a,j,b", "i,k,a,c", trA, "j,c,k,b", trB)
+    assert info.swapped == 0 and (info.Mt, info.Nt, info.Kt) == (6, 6, 6) and (info.Pr, info.Pc) == (2, 2)
+    lt = plan_target = None
+    from tiledarray_b200 import _lib as L
+    import ctypes as C
+    P = L.ContractionPlanC()
+    L.check(L.load().tadev_plan_contraction(b"i,a,j,b", b"i,k,a,c", b"j,c,k,b", C.byref(P)))
+    lt, rt = P.left_target.decode().split(","), P.right_target.decode().split(",")
+    assert set(lt[:2]) == {"i", "a"} and set(rt[2:]) == {"j", "b"} and lt[2:] == rt[:2]
+    ntl = {"i": 2, "k": 2, "a": 3, "c": 3, "j": 2, "b": 3}
+    for o in range(trA.ntiles):
+        idx = dict(zip("ikac", trA.tile_index(o)))
+        row = idx[lt[0]] * ntl[lt[1]] + idx[lt[1]]
+        col = idx[lt[2]] * ntl[lt[3]] + idx[lt[3]]
+        assert (lr[o], lc[o]) == (row, col)
+    for o in range(trB.ntiles):
+        idx = dict(zip("jckb", trB.tile_index(o)))
+        row = idx[rt[0]] * ntl[rt[1]] + idx[rt[1]]
+        col = idx[rt[2]] * ntl[rt[3]] + idx[rt[3]]
+        assert (rr[o], rc[o]) == (row, col)

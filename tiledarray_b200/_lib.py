@@ -72,7 +72,12 @@ class ArrayDescC(C.Structure):
 
 class ContractOptionsC(C.Structure):
     _fields_ = [("exchange_operands", C.c_int32), ("stream_permutes", C.c_int32), ("stream_permute_bytes", C.c_int64),
-                ("depth", C.c_int32), ("steps_per_launch", C.c_int32), ("row_blocks", C.c_int32), ("threshold", C.c_float)]
+                ("depth", C.c_int32), ("steps_per_launch", C.c_int32), ("row_blocks", C.c_int32), ("threshold", C.c_float),
+                ("mask_norms", C.POINTER(C.c_float)), ("mask_threshold", C.c_float)]
+
+
+class LayoutInfoC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("swapped", "Pr", "Pc", "Mt", "Nt", "Kt", "opA", "opB", "left_role", "right_role")]
 
 
 class ContractionInfoC(C.Structure):
@@ -95,7 +100,8 @@ class PermuteSourceC(C.Structure):
 class SummaStatsC(C.Structure):
     _fields_ = [("nsteps", C.c_int64), ("nsteps_skipped", C.c_int64), ("npairs", C.c_int64), ("nlaunches", C.c_int64),
                 ("flops", C.c_double), ("bcast_bytes", C.c_int64), ("device_ms", C.c_float), ("row_blocks", C.c_int32),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("lazy_tiles", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("lazy_tiles", C.c_int64),
+                ("gemm_ms", C.c_float), ("list_ms", C.c_float)]
 
 
 class ContractStatsC(C.Structure):
@@ -150,6 +156,9 @@ PROTOTYPES = {
     "tadev_contraction_info_get": (_i, [_vp, _P(ContractionInfoC)]),
     "tadev_contraction_owner": (_i, [_vp, _i64, _P(_i)]),
     "tadev_contraction_eval": (_i, [_vp, _vp, _i, _i, _P(ContractStatsC)]),
+    "tadev_contraction_eval_tiles": (_i, [_vp, _P(_vp), _i, _i, _P(ContractStatsC)]),
+    "tadev_contraction_layout": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, _P(ArrayDescC), _P(ArrayDescC), _P(ContractOptionsC), _i,
+                                      _P(LayoutInfoC), _vp, _vp, _vp, _vp]),
     "tadev_contraction_destroy": (_i, [_vp]),
     "tadev_elementwise_create": (_i, [_vp, _i, C.c_char_p, _d, C.c_char_p, _P(ArrayDescC), _d, C.c_char_p, _P(ArrayDescC), _f,
                                       _P(_vp)]),
@@ -160,6 +169,7 @@ PROTOTYPES = {
     "tadev_comm_unique_id": (_i, [_vp]),
     "tadev_comm_init": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "tadev_comm_destroy": (_i, [_vp]),
+    "tadev_shape_allreduce_max_f32": (_i, [_vp, _vp, _vp, _i64]),
     "tadev_bcast_panel": (_i, [_vp, _vp, _i, _i, _vp, _sz]),
     "tadev_exchange_tiles": (_i, [_vp, _vp, _i, _P(_vp), _P(_sz), _P(C.c_int32), _i, _P(_vp), _P(_sz), _P(C.c_int32)]),
     "tadev_summa_f64": (_i, [_vp, _P(SummaPlanC), _P(SummaStatsC)]),

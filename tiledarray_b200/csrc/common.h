@@ -108,6 +108,12 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
                                int ntasks, int total_cta_tiles);
 void tadev_tmap_cache_destroy(tadev_ctx* ctx);
 
+// Optional per-launch timing hook of the grouped GEMM: when set (by the SUMMA driver, on the calling thread) the
+// next launch records ev[0] immediately before and ev[1] immediately after the kernel on its stream, so the
+// kernel's own duration is measured without the descriptor upload / panel waits that precede it.
+struct GemmTimingHook { cudaEvent_t before = nullptr, after = nullptr; };
+GemmTimingHook& tadev_gemm_timing_hook();
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // CTA tile of the grouped DGEMM kernel (shared by host tile counting and the kernel)

@@ -111,7 +111,7 @@ struct Operand {
   bool dense() const { return norms.empty(); }
 };
 
-int copy_operand(const tadev_array_desc* a, Operand& o, const char* who) {
+int copy_operand(const tadev_array_desc* a, Operand& o, const char* who, bool need_tiles = true) {
   TADEV_REQUIRE(a && a->rank >= 0 && a->rank <= 16, "%s: bad array descriptor", who);
   TADEV_REQUIRE(a->rank == 0 || (a->bounds && a->ntiles), "%s: null tiling", who);
   TADEV_REQUIRE(a->memory >= 0 && a->memory <= 2, "%s: bad memory kind %d", who, a->memory);
@@ -128,7 +128,7 @@ int copy_operand(const tadev_array_desc* a, Operand& o, const char* who) {
   if (a->norms) o.norms.assign(a->norms, a->norms + n);
   if (a->tiles) o.tiles.assign(a->tiles, a->tiles + n);
   if (a->owners) o.owners.assign(a->owners, a->owners + n);
-  TADEV_REQUIRE(a->memory == TADEV_MEM_LAZY || a->tiles, "%s: null tile table", who);
+  TADEV_REQUIRE(!need_tiles || a->memory == TADEV_MEM_LAZY || a->tiles, "%s: null tile table", who);
   return TADEV_OK;
 }
 
@@ -179,10 +179,12 @@ static int build_operand_structure(Operand& o, const int32_t* perm_arr, int rank
 }
 
 // SparseShape::gemm on the device: out[Mt,Nt] = |factor| * (a .* ksz) (b .* ksz), hard-zero + count
+// followed (optionally) by SparseShape::mask (sparse_shape.h:653-676) with a user mask given in the same order
 static int device_shape_gemm(tadev_ctx* ctx, int Mt, int Nt, int Kt, const std::vector<float>& a, const std::vector<float>& b,
-                             const std::vector<float>& ksz, float abs_factor, float thr, std::vector<float>& out, uint64_t* nzero) {
+                             const std::vector<float>& ksz, float abs_factor, float thr, std::vector<float>& out, uint64_t* nzero,
+                             const float* mask = nullptr, float mask_thr = 0.0f) {
   tadev_stream s = (tadev_stream)ctx->streams[0];
-  float *d_a = nullptr, *d_b = nullptr, *d_k = nullptr, *d_o = nullptr;
+  float *d_a = nullptr, *d_b = nullptr, *d_k = nullptr, *d_o = nullptr, *d_m = nullptr;
   uint64_t* d_z = nullptr;
   const size_t na = a.size() * 4, nb = b.size() * 4, nk = ksz.size() * 4, no = (size_t)Mt * Nt * 4;
   int rc = tadev_alloc(ctx, std::max<size_t>(na, 4), (void**)&d_a, s);
@@ -195,11 +197,17 @@ static int device_shape_gemm(tadev_ctx* ctx, int Mt, int Nt, int Kt, const std::
   if (!rc && nk) rc = tadev_memcpy_h2d(ctx, d_k, ksz.data(), nk, s);
   if (!rc) rc = tadev_memset(ctx, d_z, 0, 8, s);
   if (!rc) rc = tadev_shape_gemm_f32(ctx, s, Mt, Nt, Kt, d_a, d_b, Kt ? d_k : nullptr, abs_factor, thr, d_o, d_z);
+  if (!rc && mask) {
+    rc = tadev_alloc(ctx, std::max<size_t>(no, 4), (void**)&d_m, s);
+    if (!rc) rc = tadev_memcpy_h2d(ctx, d_m, mask, no, s);
+    if (!rc) rc = tadev_shape_mask_f32(ctx, s, (int64_t)Mt * Nt, d_o, d_m, thr, mask_thr, d_z);
+  }
   out.resize((size_t)Mt * Nt);
   if (!rc) rc = tadev_memcpy_d2h(ctx, out.data(), d_o, no, s);
   if (!rc) rc = tadev_memcpy_d2h(ctx, nzero, d_z, 8, s);
   if (!rc) rc = tadev_stream_sync(ctx, s);
   tadev_free(ctx, d_a, s); tadev_free(ctx, d_b, s); tadev_free(ctx, d_k, s); tadev_free(ctx, d_o, s); tadev_free(ctx, d_z, s);
+  tadev_free(ctx, d_m, s);
   return rc;
 }
 
@@ -210,6 +218,7 @@ extern "C" int tadev_contract_options_default(tadev_contract_options* o) {
   o->stream_permutes = -1;
   o->stream_permute_bytes = (int64_t)8 << 30;
   o->threshold = 1.1920928955078125e-07f;  // SparseShape<float> default: FLT_EPSILON (sparse_shape.h:1941)
+  o->mask_threshold = o->threshold;
   return TADEV_OK;
 }
 
@@ -271,14 +280,11 @@ extern "C" int tadev_plan_general_product(const char* target, const char* left, 
   return TADEV_OK;
 }
 
-extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, const char* left_idx, const char* right_idx,
-                                        const tadev_array_desc* left, const tadev_array_desc* right, double factor,
-                                        const tadev_contract_options* options, tadev_contraction** out) {
-  TADEV_REQUIRE(ctx && target && left_idx && right_idx && left && right && out, "tadev_contraction_create: null");
-  std::unique_ptr<tadev_contraction> E(new tadev_contraction());
-  E->ctx = ctx;
-  E->factor = factor;
-  if (options) E->opt = *options; else tadev_contract_options_default(&E->opt);
+// Everything ContEngine::init_struct decides from the index lists and the tilings alone (no device work):
+// plan (+ optional operand exchange), operand structures, GemmHelper ranges, fused extents, result tiling.
+static int plan_structure(tadev_contraction* Ep, int nranks, const char* target, const char* left_idx, const char* right_idx,
+                          const tadev_array_desc* left, const tadev_array_desc* right, bool need_tiles) {
+  tadev_contraction* E = Ep;
   int rc;
   {
     int32_t nfused = 0;
@@ -290,8 +296,8 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
   }
   if (rc) return rc;
   const tadev_contraction_plan& P = E->plan;
-  if ((rc = copy_operand(E->swapped ? right : left, E->L, "tadev_contraction_create(left)"))) return rc;
-  if ((rc = copy_operand(E->swapped ? left : right, E->R, "tadev_contraction_create(right)"))) return rc;
+  if ((rc = copy_operand(E->swapped ? right : left, E->L, "tadev_contraction_create(left)", need_tiles))) return rc;
+  if ((rc = copy_operand(E->swapped ? left : right, E->R, "tadev_contraction_create(right)", need_tiles))) return rc;
   TADEV_REQUIRE(E->L.tr.rank() == P.left_rank && E->R.tr.rank() == P.right_rank, "index list rank does not match the array");
   TADEV_REQUIRE(E->L.d.memory != TADEV_MEM_HOST || P.perm_left[0] < 0, "host-resident left operand needs an explicit permutation: not supported");
   TADEV_REQUIRE(E->R.d.memory != TADEV_MEM_HOST || P.perm_right[0] < 0, "host-resident right operand needs an explicit permutation: not supported");
@@ -311,7 +317,7 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
     // ranges in the canonical layouts: left (H, outer, K), right (H, K, outer)
     const int nh = E->nh;
     TADEV_REQUIRE(E->L.d.memory == TADEV_MEM_DEVICE && E->R.d.memory == TADEV_MEM_DEVICE, "general products take device-resident arrays");
-    TADEV_REQUIRE(ctx->nranks == 1, "general (fused-index) products are evaluated on one rank in this version");
+    TADEV_REQUIRE(nranks == 1, "general (fused-index) products are evaluated on one rank in this version");
     E->lo[0] = nh; E->lo[1] = E->li[0] = lr - nc; E->li[1] = lr;
     E->ri[0] = nh; E->ri[1] = E->ro[0] = nh + nc; E->ro[1] = rr;
     for (int d = 0; d < nh; ++d) TADEV_REQUIRE(trA.b[d] == trB.b[d], "general product: the fused tiled ranges are not congruent");
@@ -334,11 +340,80 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
     E->tr_target.b.resize(P.result_rank);
     for (int i = 0; i < P.result_rank; ++i) E->tr_target.b[E->perm_res[i]] = E->tr_gemm.b[i];
   }
+  return TADEV_OK;
+}
+
+// [host] Where SUMMA wants the operand tiles of this expression: the process grid ProcGrid chooses for the
+// result and, for every tile of each USER operand (original tiling, row-major ordinal), its position in the
+// fused GEMM-side tile grid. The tile belongs on rank (frow % Pr) * Pc + fcol % Pc (proc_grid.h:566-597); an
+// arena ordered by (fcol, frow) for the GEMM's left operand and by (frow, fcol) for the right one makes every
+// SUMMA panel a contiguous byte range. role[x] = 0: operand x is the GEMM's left operand A(i,k), 1: right B(k,j)
+// (the engine may exchange the operands). Arrays created this way need no redistribution.
+extern "C" int tadev_contraction_layout(const char* target, const char* left_idx, const char* right_idx,
+                                        const tadev_array_desc* left, const tadev_array_desc* right,
+                                        const tadev_contract_options* options, int nranks, tadev_contraction_layout_info* info,
+                                        int32_t* left_frow, int32_t* left_fcol, int32_t* right_frow, int32_t* right_fcol) {
+  TADEV_REQUIRE(target && left_idx && right_idx && left && right && info && nranks >= 1, "tadev_contraction_layout: bad args");
+  std::unique_ptr<tadev_contraction> E(new tadev_contraction());
+  if (options) E->opt = *options; else tadev_contract_options_default(&E->opt);
+  int rc = plan_structure(E.get(), nranks, target, left_idx, right_idx, left, right, false);
+  if (rc) return rc;
+  memset(info, 0, sizeof(*info));
+  info->swapped = E->swapped; info->Mt = E->Mt; info->Nt = E->Nt; info->Kt = E->Kt;
+  info->opA = E->plan.opA; info->opB = E->plan.opB;
+  info->left_role = E->swapped ? 1 : 0; info->right_role = E->swapped ? 0 : 1;
+  info->Pr = info->Pc = 1;
+  if (nranks > 1) {
+    tadev_proc_grid g;
+    const int64_t msum = std::accumulate(E->m_ext.begin(), E->m_ext.end(), (int64_t)0), nsum = std::accumulate(E->n_ext.begin(), E->n_ext.end(), (int64_t)0);
+    if ((rc = tadev_proc_grid_make(0, nranks, E->Mt, E->Nt, msum, nsum, &g))) return rc;
+    info->Pr = g.proc_rows; info->Pc = g.proc_cols;
+  }
+  for (int side = 0; side < 2; ++side) {
+    const Operand& o = side == 0 ? E->L : E->R;  // GEMM side
+    const bool user_left = (side == 0) != (E->swapped != 0);
+    int32_t* frow = user_left ? left_frow : right_frow;
+    int32_t* fcol = user_left ? left_fcol : right_fcol;
+    if (!frow || !fcol) continue;
+    const bool op_n = (side == 0 ? E->plan.opA : E->plan.opB) == TADEV_OP_N;
+    const int64_t rows = (int64_t)(E->general ? E->Ht : 1) * (side == 0 ? E->Mt : E->Kt), cols = side == 0 ? E->Kt : E->Nt;
+    const int R = o.tr.rank();
+    const std::vector<int64_t> tshape = o.tr.tiles_shape(), pshape = o.ptr.tiles_shape();
+    std::vector<int64_t> idx, pidx(R);
+    for (int64_t ord = 0; ord < o.tr.total(); ++ord) {
+      int64_t po = ord;
+      if (!o.perm.empty()) {
+        unravel(ord, tshape, idx);
+        for (int i = 0; i < R; ++i) pidx[o.perm[i]] = idx[i];
+        po = ravel(pidx, pshape);
+      }
+      const int64_t pos = op_n ? po : (po % rows) * cols + po / rows;  // == fused_pos()
+      frow[ord] = (int32_t)(pos / cols); fcol[ord] = (int32_t)(pos % cols);
+    }
+  }
+  return TADEV_OK;
+}
+
+extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, const char* left_idx, const char* right_idx,
+                                        const tadev_array_desc* left, const tadev_array_desc* right, double factor,
+                                        const tadev_contract_options* options, tadev_contraction** out) {
+  TADEV_REQUIRE(ctx && target && left_idx && right_idx && left && right && out, "tadev_contraction_create: null");
+  std::unique_ptr<tadev_contraction> E(new tadev_contraction());
+  E->ctx = ctx;
+  E->factor = factor;
+  if (options) E->opt = *options; else tadev_contract_options_default(&E->opt);
+  int rc = plan_structure(E.get(), ctx->nranks, target, left_idx, right_idx, left, right, true);
+  if (rc) return rc;
+  const tadev_contraction_plan& P = E->plan;
+  const int nc = P.inner_rank;
+  const TRange& trA = E->L.ptr;
 
   // result shape (make_shape): sparse x sparse -> device screening
   E->sparse = !(E->L.dense() && E->R.dense());
   const float thr = E->opt.threshold;
+  TADEV_REQUIRE(E->sparse || !E->opt.mask_norms, "set_shape: a result mask needs block-sparse operands (the dense policy has no shape override)");
   if (E->sparse) {
+    // (the reference static_asserts that both arguments use the same policy, expressions/mult_engine.h:112-115)
     TADEV_REQUIRE(!E->L.dense() && !E->R.dense(), "mixed dense/sparse contraction is not supported");
     const int Mt = E->Mt, Nt = E->Nt, Kt = E->Kt;
     // 2-D views in GEMM orientation
@@ -350,8 +425,22 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
     else for (int j = 0; j < Nt; ++j) for (int k = 0; k < Kt; ++k) E->b_n[(size_t)k * Nt + j] = E->R.pnorms[(size_t)j * Kt + k];
     std::vector<float> ksz;
     if (nc > 0) ksz = recursive_outer(trA, E->li[0], E->li[1]);
+    // user result mask (Expr::set_shape, expressions/expr.h:116; applied after make_shape, cont_engine.h:526-528):
+    // given over the TARGET tile grid, brought to GEMM order for the device kernel
+    std::vector<float> mask_g;
+    if (E->opt.mask_norms) {
+      const int64_t nt = E->tr_target.total();
+      mask_g.assign(E->opt.mask_norms, E->opt.mask_norms + nt);
+      if (!E->perm_res.empty()) {
+        std::vector<int> inv(E->perm_res.size());
+        for (size_t a = 0; a < E->perm_res.size(); ++a) inv[E->perm_res[a]] = (int)a;
+        mask_g = permute_norms(mask_g, E->tr_target.tiles_shape(), inv);
+      }
+      E->opt.mask_norms = nullptr;  // the caller's array is not kept
+    }
     if (!E->general) {
-      rc = device_shape_gemm(ctx, Mt, Nt, nc > 0 ? Kt : 0, E->a_n, E->b_n, ksz, (float)std::fabs(factor), thr, E->c_n, &E->nzero);
+      rc = device_shape_gemm(ctx, Mt, Nt, nc > 0 ? Kt : 0, E->a_n, E->b_n, ksz, (float)std::fabs(factor), thr, E->c_n, &E->nzero,
+                             mask_g.empty() ? nullptr : mask_g.data(), E->opt.mask_threshold);
       if (rc) return rc;
     } else {
       // SparseShape::gemm_batched (sparse_shape.h:1707-1900): every fused-index slab is a norm GEMM with the
@@ -363,7 +452,8 @@ extern "C" int tadev_contraction_create(tadev_ctx* ctx, const char* target, cons
         std::copy(E->a_n.begin() + (size_t)h * Mt * Kt, E->a_n.begin() + (size_t)(h + 1) * Mt * Kt, as.begin());
         std::copy(E->b_n.begin() + (size_t)h * Kt * Nt, E->b_n.begin() + (size_t)(h + 1) * Kt * Nt, bs.begin());
         uint64_t nz = 0;
-        rc = device_shape_gemm(ctx, Mt, Nt, nc > 0 ? Kt : 0, as, bs, ksz, (float)std::fabs(factor), thr, cs, &nz);
+        rc = device_shape_gemm(ctx, Mt, Nt, nc > 0 ? Kt : 0, as, bs, ksz, (float)std::fabs(factor), thr, cs, &nz,
+                               mask_g.empty() ? nullptr : mask_g.data() + (size_t)h * Mt * Nt, E->opt.mask_threshold);
         if (rc) return rc;
         std::copy(cs.begin(), cs.end(), E->c_n.begin() + (size_t)h * Mt * Nt);
         E->nzero += nz;
@@ -636,17 +726,40 @@ int build_view(tadev_contraction* E, Operand& o, bool is_left, View& v, float* p
 
 }  // namespace
 
-extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, int result_memory, int accumulate,
-                                      tadev_contract_stats* stats) {
-  TADEV_REQUIRE(E && result_arena, "tadev_contraction_eval: null");
+// Evaluate into caller-owned result tiles: result_tiles[t] is the storage of local result tile t of the info
+// struct (ordinals[t], elems[t]), device or pinned host memory. With accumulate != 0 the tiles hold the previous
+// contents of c and the product is added (c("m,n") += a("m,k") * b("k,n")): the existing array's own tile
+// pointers are used, whatever its arena layout is.
+extern "C" int tadev_contraction_eval_tiles(tadev_contraction* E, void* const* result_tiles, int result_memory, int accumulate,
+                                            tadev_contract_stats* stats) {
+  TADEV_REQUIRE(E && (result_tiles || E->keys.empty()), "tadev_contraction_eval_tiles: null");
   TADEV_REQUIRE(result_memory == TADEV_MEM_DEVICE || result_memory == TADEV_MEM_HOST, "tadev_contraction_eval: the result must be device- or host-resident");
-  TADEV_REQUIRE(result_memory == TADEV_MEM_DEVICE || E->perm_res.empty(), "host-resident result needs a result permutation: not supported");
-  TADEV_REQUIRE(!accumulate || E->perm_res.empty(), "accumulating into a result that needs a permutation is not supported");
+  const bool permuted = !E->perm_res.empty();
+  TADEV_REQUIRE(!(permuted && accumulate && result_memory == TADEV_MEM_HOST),
+                "accumulating into a host-resident result that needs a result permutation is not supported");
+  for (size_t t = 0; t < E->keys.size(); ++t) TADEV_REQUIRE(result_tiles[t], "tadev_contraction_eval_tiles: result tile %zu has no storage", t);
   tadev_ctx* ctx = E->ctx;
   tadev_stream s = (tadev_stream)ctx->streams[0];
   if (stats) memset(stats, 0, sizeof(*stats));
   float permute_ms = 0.0f;
   View vA, vB;
+  double *gemm_arena = nullptr, *perm_arena = nullptr;
+  // every exit path releases the temporaries (stream-ordered frees on the compute stream)
+  struct Cleanup {
+    tadev_ctx* ctx; tadev_stream s; View *a, *b; double **g, **p; tadev_contraction* E;
+    ~Cleanup() {
+      if (a->tmp_arena) tadev_free(ctx, a->tmp_arena, s);
+      if (b->tmp_arena) tadev_free(ctx, b->tmp_arena, s);
+      if (*g) tadev_free(ctx, *g, s);
+      if (*p) tadev_free(ctx, *p, s);
+      // the received copies of redistributed operand tiles were only needed for this evaluation
+      for (Operand* o : {&E->L, &E->R}) {
+        if (o->redist_arena) { tadev_free(ctx, o->redist_arena, s); o->redist_arena = nullptr; }
+        if (!o->tiles_before.empty()) { o->tiles.swap(o->tiles_before); o->tiles_before.clear(); }
+        o->redistributed = false;
+      }
+    }
+  } cleanup{ctx, s, &vA, &vB, &gemm_arena, &perm_arena, E};
   int rc = redistribute_operand(E, E->L, true);
   if (!rc) rc = redistribute_operand(E, E->R, false);
   if (rc) return rc;
@@ -654,22 +767,25 @@ extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, 
   if (!rc) rc = build_view(E, E->R, false, vB, &permute_ms);
   if (rc) return rc;
 
-  // result tiles in GEMM order: straight into the caller's arena, or into a temporary one that is
-  // permuted into the caller's arena afterwards
-  double* gemm_arena = static_cast<double*>(result_arena);
-  if (!E->perm_res.empty()) {
+  // result tiles in GEMM order: straight into the caller's tiles, or into a temporary device arena that is
+  // permuted into the caller's tiles afterwards (ContractReduce's post-process, contract_reduce.h:370-378)
+  std::vector<double*> c_tab((size_t)std::max<int64_t>((int64_t)E->Ht * E->Mt * E->Nt, 1), nullptr);
+  if (permuted) {
     rc = tadev_alloc(ctx, (size_t)E->arena_elems * 8, (void**)&gemm_arena, s);
     if (rc) return rc;
+    for (size_t t = 0; t < E->keys.size(); ++t) c_tab[E->keys[t]] = gemm_arena + E->offs[t];
+  } else {
+    for (size_t t = 0; t < E->keys.size(); ++t) c_tab[E->keys[t]] = static_cast<double*>(result_tiles[t]);
   }
-  std::vector<double*> c_tab((size_t)std::max<int64_t>((int64_t)E->Ht * E->Mt * E->Nt, 1), nullptr);
-  for (size_t t = 0; t < E->keys.size(); ++t) c_tab[E->keys[t]] = gemm_arena + E->offs[t];
+  const int gemm_memory = permuted ? TADEV_MEM_DEVICE : result_memory;
+  const int gemm_accumulate = permuted ? 0 : (accumulate ? 1 : 0);
 
   tadev_summa_stats st{};
   if (E->general) {
     // BatchedContractReduce (tile_op/batched_contract_reduce.h) for every result tile of every fused slab,
     // in ONE grouped launch: batch element e of tile (h,i,j) is its own group — C + e*m*n accumulates
     // A(h,i,k)[e] * B(h,k,j)[e] over the contracted tiles k (a tile (nb, m, k) is nb row-major m x k matrices).
-    TADEV_REQUIRE(result_memory == TADEV_MEM_DEVICE, "general products produce device-resident results");
+    TADEV_REQUIRE(gemm_memory == TADEV_MEM_DEVICE, "general products produce device-resident results");
     std::vector<tadev_gemm_group> groups;
     std::vector<tadev_gemm_task> tasks;
     const float thr = E->opt.threshold;
@@ -679,7 +795,7 @@ extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, 
       const int h = (int)(key / ((int64_t)Mt * Nt)), i = (int)((key / Nt) % Mt), j = (int)(key % Nt);
       const int64_t m = E->m_ext[i], n = E->n_ext[j], nb = E->h_ext[h];
       for (int64_t e = 0; e < nb; ++e) {
-        tadev_gemm_group G{c_tab[key] + e * m * n, (int32_t)m, (int32_t)n, (int32_t)tasks.size(), 0, accumulate ? 1 : 0, 0};
+        tadev_gemm_group G{c_tab[key] + e * m * n, (int32_t)m, (int32_t)n, (int32_t)tasks.size(), 0, gemm_accumulate, 0};
         for (int k = 0; k < Kt; ++k) {
           const size_t ak = ((size_t)h * Mt + i) * Kt + k, bk = ((size_t)h * Kt + k) * Nt + j;
           if (E->sparse && (E->a_n[ak] < thr || E->b_n[bk] < thr)) continue;
@@ -702,32 +818,30 @@ extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, 
     float ms = 0;
     tadev_event_elapsed_ms(ctx, e0, e1, &ms);
     tadev_event_destroy(ctx, e0); tadev_event_destroy(ctx, e1);
-    st.nsteps = Kt; st.nlaunches = groups.empty() ? 0 : 1; st.device_ms = ms; st.row_blocks = 1;
+    st.nsteps = Kt; st.nlaunches = groups.empty() ? 0 : 1; st.device_ms = ms; st.gemm_ms = ms; st.row_blocks = 1;
   } else {
-  tadev_summa_plan sp{};
-  sp.Mt = E->Mt; sp.Nt = E->Nt; sp.Kt = E->Kt;
-  sp.m_ext = E->m_ext.data(); sp.n_ext = E->n_ext.data(); sp.k_ext = E->k_ext.data();
-  sp.opA = E->plan.opA; sp.opB = E->plan.opB; sp.alpha = E->factor;
-  sp.a_norms = E->sparse ? E->a_n.data() : nullptr;
-  sp.b_norms = E->sparse ? E->b_n.data() : nullptr;
-  sp.c_norms = E->sparse ? E->c_n.data() : nullptr;
-  sp.threshold = E->opt.threshold;
-  sp.a_tiles = vA.table.data(); sp.b_tiles = vB.table.data(); sp.c_tiles = c_tab.data();
-  sp.accumulate = accumulate ? 1 : 0;
-  sp.depth = E->opt.depth; sp.steps_per_launch = E->opt.steps_per_launch; sp.row_blocks = E->opt.row_blocks;
-  sp.flags = (E->L.d.memory == TADEV_MEM_HOST ? TADEV_SUMMA_A_ON_HOST : 0) | (E->R.d.memory == TADEV_MEM_HOST ? TADEV_SUMMA_B_ON_HOST : 0) |
-             (result_memory == TADEV_MEM_HOST ? TADEV_SUMMA_C_ON_HOST : 0) | (vA.lazy ? TADEV_SUMMA_A_LAZY : 0) | (vB.lazy ? TADEV_SUMMA_B_LAZY : 0);
-  if (vA.lazy) { sp.a_provider = vA.provider; sp.a_user = vA.user(); }
-  if (vB.lazy) { sp.b_provider = vB.provider; sp.b_user = vB.user(); }
-  rc = tadev_summa_f64(ctx, &sp, &st);
+    tadev_summa_plan sp{};
+    sp.Mt = E->Mt; sp.Nt = E->Nt; sp.Kt = E->Kt;
+    sp.m_ext = E->m_ext.data(); sp.n_ext = E->n_ext.data(); sp.k_ext = E->k_ext.data();
+    sp.opA = E->plan.opA; sp.opB = E->plan.opB; sp.alpha = E->factor;
+    sp.a_norms = E->sparse ? E->a_n.data() : nullptr;
+    sp.b_norms = E->sparse ? E->b_n.data() : nullptr;
+    sp.c_norms = E->sparse ? E->c_n.data() : nullptr;
+    sp.threshold = E->opt.threshold;
+    sp.a_tiles = vA.table.data(); sp.b_tiles = vB.table.data(); sp.c_tiles = c_tab.data();
+    sp.accumulate = gemm_accumulate;
+    sp.depth = E->opt.depth; sp.steps_per_launch = E->opt.steps_per_launch; sp.row_blocks = E->opt.row_blocks;
+    sp.flags = (E->L.d.memory == TADEV_MEM_HOST ? TADEV_SUMMA_A_ON_HOST : 0) | (E->R.d.memory == TADEV_MEM_HOST ? TADEV_SUMMA_B_ON_HOST : 0) |
+               (gemm_memory == TADEV_MEM_HOST ? TADEV_SUMMA_C_ON_HOST : 0) | (vA.lazy ? TADEV_SUMMA_A_LAZY : 0) | (vB.lazy ? TADEV_SUMMA_B_LAZY : 0);
+    if (vA.lazy) { sp.a_provider = vA.provider; sp.a_user = vA.user(); }
+    if (vB.lazy) { sp.b_provider = vB.provider; sp.b_user = vB.user(); }
+    rc = tadev_summa_f64(ctx, &sp, &st);
   }
-  if (vA.tmp_arena) tadev_free(ctx, vA.tmp_arena, s);
-  if (vB.tmp_arena) tadev_free(ctx, vB.tmp_arena, s);
-  if (rc) { if (gemm_arena != result_arena) tadev_free(ctx, gemm_arena, s); return rc; }
+  if (rc) return rc;
 
-  // result permutation: ContractReduce's post-process (contract_reduce.h:370-378), batched per extent.
-  // The target arena uses the same per-tile offsets (a permuted tile has the same volume).
-  if (!E->perm_res.empty()) {
+  // result permutation, batched per tile extent; then (+=) the permuted product is added to the existing
+  // tiles, or (host-resident result) copied back tile by tile
+  if (permuted) {
     void *e0 = nullptr, *e1 = nullptr;
     tadev_event_create(ctx, &e0); tadev_event_create(ctx, &e1);
     tadev_event_record(ctx, e0, s);
@@ -738,38 +852,54 @@ extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, 
       unravel(E->keys[t], gshape, gidx);
       for (int d = 0; d < R; ++d) exts[t * R + d] = E->tr_gemm.ext(d, gidx[d]);
     }
+    const bool direct = !accumulate && result_memory == TADEV_MEM_DEVICE;
+    if (!direct) {
+      rc = tadev_alloc(ctx, (size_t)E->arena_elems * 8, (void**)&perm_arena, s);
+      if (rc) { tadev_event_destroy(ctx, e0); tadev_event_destroy(ctx, e1); return rc; }
+    }
     std::vector<char> done(E->keys.size(), 0);
     std::vector<const void*> ins;
     std::vector<void*> outs;
     std::vector<int32_t> perm32(E->perm_res.begin(), E->perm_res.end());
-    double* target = static_cast<double*>(result_arena);
     for (size_t t = 0; t < E->keys.size() && !rc; ++t) {
       if (done[t]) continue;
       ins.clear(); outs.clear();
       for (size_t q = t; q < E->keys.size(); ++q) {
         if (done[q] || memcmp(&exts[q * R], &exts[t * R], sizeof(int64_t) * R) != 0) continue;
         ins.push_back(gemm_arena + E->offs[q]);
-        outs.push_back(target + E->offs[q]);
+        outs.push_back(direct ? result_tiles[q] : (void*)(perm_arena + E->offs[q]));
         done[q] = 1;
       }
       rc = tadev_permute_batched(ctx, s, R, &exts[t * R], perm32.data(), 8, (int)ins.size(), ins.data(), outs.data());
+    }
+    if (!rc && !direct && result_memory == TADEV_MEM_DEVICE && !E->keys.empty()) {  // c += permuted product
+      std::vector<double*> out(E->keys.size());
+      std::vector<const double*> x(E->keys.size()), y(E->keys.size());
+      for (size_t t = 0; t < E->keys.size(); ++t) { out[t] = static_cast<double*>(result_tiles[t]); x[t] = out[t]; y[t] = perm_arena + E->offs[t]; }
+      rc = tadev_tiles_binary_f64(ctx, s, TADEV_EW_AXPBY, (int)out.size(), out.data(), x.data(), y.data(), E->elems.data(), 1.0, 1.0);
+    }
+    if (!rc && !direct && result_memory == TADEV_MEM_HOST) {
+      for (size_t t = 0; t < E->keys.size() && !rc; ++t)
+        rc = tadev_memcpy_d2h(ctx, result_tiles[t], perm_arena + E->offs[t], (size_t)E->elems[t] * 8, s);
+      if (!rc) rc = tadev_stream_sync(ctx, s);
     }
     tadev_event_record(ctx, e1, s);
     float ms = 0;
     tadev_event_elapsed_ms(ctx, e0, e1, &ms);
     tadev_event_destroy(ctx, e0); tadev_event_destroy(ctx, e1);
     permute_ms += ms;
-    tadev_free(ctx, gemm_arena, s);
     if (rc) return rc;
-  }
-  // the received copies of redistributed operand tiles were only needed for this evaluation
-  for (Operand* o : {&E->L, &E->R}) {
-    if (o->redist_arena) { tadev_free(ctx, o->redist_arena, s); o->redist_arena = nullptr; }
-    if (!o->tiles_before.empty()) { o->tiles.swap(o->tiles_before); o->tiles_before.clear(); }
-    o->redistributed = false;
   }
   if (stats) { stats->summa = st; stats->permute_ms = permute_ms; }
   return TADEV_OK;
+}
+
+extern "C" int tadev_contraction_eval(tadev_contraction* E, void* result_arena, int result_memory, int accumulate,
+                                      tadev_contract_stats* stats) {
+  TADEV_REQUIRE(E && result_arena, "tadev_contraction_eval: null");
+  std::vector<void*> tiles(E->keys.size());
+  for (size_t t = 0; t < E->keys.size(); ++t) tiles[t] = static_cast<double*>(result_arena) + E->offs[t];
+  return tadev_contraction_eval_tiles(E, tiles.data(), result_memory, accumulate, stats);
 }
 
 // =================================================================================================
@@ -857,6 +987,20 @@ extern "C" int tadev_elementwise_create(tadev_ctx* ctx, int op, const char* targ
   if (b) {
     TADEV_REQUIRE(E->B.ptr.b == E->tr.b, "element-wise expression: operand tilings differ");
     TADEV_REQUIRE(E->A.dense() == E->B.dense(), "mixed dense/sparse element-wise expression is not supported");
+    if (ctx->nranks > 1) {
+      // a tile held by another rank must not be mistaken for a zero tile: both operands need the same process
+      // map (the reference redistributes through the result pmap; this engine does not move element-wise operands)
+      const int64_t nt = E->tr.total();
+      for (int64_t o = 0; o < nt; ++o) {
+        const bool za = !E->A.dense() && E->A.norms[o] < threshold, zb = !E->B.dense() && E->B.norms[o] < threshold;
+        if (za || zb) continue;
+        if (!E->A.owners.empty() && !E->B.owners.empty())
+          TADEV_REQUIRE(E->A.owners[o] == E->B.owners[o], "multi-rank element-wise expression: tile %lld lives on rank %d in one operand and on rank %d in the other",
+                        (long long)o, E->A.owners[o], E->B.owners[o]);
+        TADEV_REQUIRE((E->A.tiles[o] != nullptr) == (E->B.tiles[o] != nullptr),
+                      "multi-rank element-wise expression: tile %lld is local in only one operand (the operands need identical process maps)", (long long)o);
+      }
+    }
   }
   E->sparse = !E->A.dense();
   const int64_t n = E->tr.total();

@@ -14,6 +14,11 @@ void tadev_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* tadev_last_error(void) { return g_err; }
+
+GemmTimingHook& tadev_gemm_timing_hook() {
+  static thread_local GemmTimingHook hook;
+  return hook;
+}
 extern "C" const char* tadev_version(void) { return "tadev 0.1 (sm_100a)"; }
 
 extern "C" int tadev_device_count(int* n) {

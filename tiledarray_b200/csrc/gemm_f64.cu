@@ -235,13 +235,14 @@ int launch_variant(cudaStream_t s, const tadev_gemm_group* d_groups, int ngroups
                    const tadev_gemm_task* d_tasks, const int32_t* d_tile_prefix, int total_cta_tiles,
                    double alpha) {
   auto kern = gemm_grouped_f64_kernel<OPA, OPB, VEC>;
-  static bool attr_set = false;  // benign race: idempotent
-  if (!attr_set) {
-    TADEV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  // per-device attribute: set on every launch (see gemm_f64_ws.cu)
+  TADEV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GemmTimingHook& hook = tadev_gemm_timing_hook();
+  if (hook.before) TADEV_CHECK_CUDA(cudaEventRecord(hook.before, s));
   kern<<<total_cta_tiles, NTHREADS, SMEM_BYTES, s>>>(d_groups, ngroups, d_tasks, d_tile_prefix, alpha);
   TADEV_CHECK_CUDA(cudaGetLastError());
+  if (hook.after) TADEV_CHECK_CUDA(cudaEventRecord(hook.after, s));
+  hook.before = hook.after = nullptr;
   return TADEV_OK;
 }
 

@@ -5,7 +5,7 @@
 // kernels.h:92-231 -> math/blas.h:171-177), used when every operand row is 16-byte aligned
 // (even leading dimensions — the common case).
 //
-// Structure (one CTA per SM, 288 threads):
+// Structure (one CTA per SM, 384 threads = 3 warpgroups):
 //   warp 8      producer (warps 9-11 idle, their registers go to the consumers): pulls CTA tiles from a global atomic counter (dynamic scheduling evens
 //               out block-sparse groups of different K), finds the owning group by a
 //               warp-cooperative 32-ary search, and streams operand slabs of 16 k-values into a
@@ -488,13 +488,15 @@ template <int OPA, int OPB>
 int launch_ws_variant(cudaStream_t s, int grid, const tadev_gemm_group* d_groups, int ngroups, const WsTask* d_tasks,
                       const int2* d_items, int total_tiles, int* d_counter, double alpha, int static_sched, int wave_sync) {
   auto kern = gemm_grouped_f64_ws_kernel<OPA, OPB>;
-  static bool attr_set = false;  // benign race: idempotent
-  if (!attr_set) {
-    TADEV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  // the attribute is per device (context): set it on every launch (a cheap host-side call) rather than once per
+  // process, so a process driving several devices gets the opt-in on each of them
+  TADEV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GemmTimingHook& hook = tadev_gemm_timing_hook();
+  if (hook.before) TADEV_CHECK_CUDA(cudaEventRecord(hook.before, s));
   kern<<<grid, NTHREADS, SMEM_BYTES, s>>>(d_groups, ngroups, d_tasks, d_items, total_tiles, d_counter, alpha, static_sched, wave_sync);
   TADEV_CHECK_CUDA(cudaGetLastError());
+  if (hook.after) TADEV_CHECK_CUDA(cudaEventRecord(hook.after, s));
+  hook.before = hook.after = nullptr;
   return TADEV_OK;
 }
 

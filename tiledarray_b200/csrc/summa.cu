@@ -17,7 +17,9 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <numeric>
+#include <string>
 
 #include "common.h"
 #include "summa_schedule.h"
@@ -54,6 +56,12 @@ extern "C" int tadev_comm_init(tadev_ctx* ctx, const void* unique_id128, int ran
   if (const char* e = getenv("TADEV_SM_RESERVE")) ctx->gemm_sm_reserve = atoi(e);
   ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
   if (ctx->gemm_sm_reserve > 0) { cfg.minCTAs = 1; cfg.maxCTAs = ctx->gemm_sm_reserve; }
+  // NCCL's default on sm_90+ launches its CTAs as thread-block clusters of 4, which must be co-scheduled inside
+  // one GPC: the few SMs the persistent GEMM leaves free are spread over the GPCs, so a clustered broadcast
+  // kernel could not start before the GEMM's CTAs exited and every other window's panel traffic was exposed
+  // (profiles/r02_n4_trace_cga4.log: bcast_done of windows 2n, 2n+1 7 ms after gemm_done of window 2n-1).
+  cfg.cgaClusterSize = 1;
+  if (const char* e = getenv("TADEV_NCCL_CGA")) cfg.cgaClusterSize = atoi(e);
   TADEV_CHECK_NCCL(ncclCommInitRankConfig(&ctx->world, nranks, id, rank, &cfg));
   ctx->rank = rank; ctx->nranks = nranks; ctx->Pr = Pr; ctx->Pc = Pc;
   const bool in_grid = rank < Pr * Pc;
@@ -100,6 +108,16 @@ extern "C" int tadev_bcast_panel(tadev_ctx* ctx, tadev_stream s, int which, int 
   TADEV_REQUIRE(comm, "tadev_bcast_panel: communicators not initialised (or rank outside the grid)");
   if (bytes == 0) return TADEV_OK;
   TADEV_CHECK_NCCL(ncclBroadcast(d_buf, d_buf, bytes, ncclChar, root, comm, (cudaStream_t)s));
+  return TADEV_OK;
+}
+
+// Shape replication (SparseShape ctor with a World: world.gop.max over the tile norms, sparse_shape.h:416):
+// every rank contributes the norms of its own tiles (zeros elsewhere); afterwards all ranks hold all norms.
+extern "C" int tadev_shape_allreduce_max_f32(tadev_ctx* ctx, tadev_stream s, float* d_norms, int64_t n) {
+  TADEV_REQUIRE(ctx && n >= 0, "tadev_shape_allreduce_max_f32: bad args");
+  if (n == 0 || ctx->nranks == 1) return TADEV_OK;
+  TADEV_REQUIRE(ctx->world && d_norms, "tadev_shape_allreduce_max_f32: communicators not initialised");
+  TADEV_CHECK_NCCL(ncclAllReduce(d_norms, d_norms, (size_t)n, ncclFloat, ncclMax, ctx->world, (cudaStream_t)s));
   return TADEV_OK;
 }
 
@@ -248,6 +266,26 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
     b_cache = k_sum * n_max * 8.0 <= limit;
   }
 
+  // Pipeline policy. The reference keeps `depth` SUMMA iterations in flight (contraction_eval.h:1925-1977: at least 2,
+  // boosted by the sparsity of the arguments, bounded by TA_SUMMA_MAX_DEPTH and by TA_SUMMA_MAX_MEMORY through
+  // mem_bound_depth, :225-263). Here D ring slots of W steps each are in flight (one grouped GEMM launch per window):
+  // W = ceil(4096 contracted elements / average k extent), multiplied by the reference's sparse boost
+  // 1 - 1.35638 log2((1 - min(sA, 0.9)) (1 - min(sB, 0.9))); D * W <= TA_SUMMA_MAX_DEPTH; D * window bytes <=
+  // TA_SUMMA_MAX_MEMORY (same syntax as the reference: "<number> [kB|KiB|MB|MiB|GB|GiB]", at least 100 MiB).
+  X.D = std::max(2, P.depth > 0 ? P.depth : 2);
+  size_t kMaxWindowBytes = size_t(5) << 30;
+  if (const char* e = getenv("TA_SUMMA_MAX_MEMORY")) {
+    char unit[16] = "";
+    double mem = 0.0;
+    if (sscanf(e, "%lf %15s", &mem, unit) >= 1 && mem > 0.0) {
+      const std::string u(unit);
+      if (u == "KB" || u == "kB") mem *= 1e3; else if (u == "KiB" || u == "kiB") mem *= 1024.0;
+      else if (u == "MB") mem *= 1e6; else if (u == "MiB") mem *= 1048576.0;
+      else if (u == "GB") mem *= 1e9; else if (u == "GiB") mem *= 1073741824.0;
+      mem = std::max(mem, 104857600.0);
+      kMaxWindowBytes = std::min<size_t>(kMaxWindowBytes, (size_t)(mem / X.D));
+    }
+  }
   W = P.steps_per_launch;
   if (W <= 0) {
     if (!multi && !a_stg && !b_stg) W = std::max(1, Kt);
@@ -255,12 +293,20 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
       double avgk = 0;
       for (int k = 0; k < Kt; ++k) avgk += (double)P.k_ext[k];
       avgk = Kt ? avgk / Kt : 1.0;
-      W = (int)std::min<double>(64.0, std::max(1.0, std::ceil(4096.0 / std::max(1.0, avgk))));
+      double w = std::max(1.0, std::ceil(4096.0 / std::max(1.0, avgk)));
+      if (P.a_norms && P.b_norms && Mt > 0 && Nt > 0 && Kt > 0) {
+        size_t za = 0, zb = 0;
+        for (size_t x = 0; x < (size_t)Mt * Kt; ++x) za += P.a_norms[x] < P.threshold;
+        for (size_t x = 0; x < (size_t)Kt * Nt; ++x) zb += P.b_norms[x] < P.threshold;
+        const float sa = (float)za / ((float)Mt * Kt), sb = (float)zb / ((float)Kt * Nt);
+        const float frac = (1.0f - std::min(sa, 0.9f)) * (1.0f - std::min(sb, 0.9f));
+        w = w * (1.0 - 1.35638 * std::log2((double)frac)) + 0.5;
+      }
+      W = (int)std::min<double>(64.0, std::max(1.0, std::floor(w)));
+      if (const char* e = getenv("TADEV_SUMMA_W")) if (atoi(e) > 0) W = atoi(e);
     }
+    if (const char* e = getenv("TA_SUMMA_MAX_DEPTH")) if (atoi(e) > 0) W = std::max(1, std::min(W, atoi(e) / X.D));
   }
-  const size_t kMaxWindowBytes = size_t(5) << 30;
-  X.D = std::max(2, P.depth > 0 ? P.depth : 2);
-
   // ---- per-block step views and windows
   auto tile_a_elems = [&](int i, int k) { return (size_t)P.m_ext[i] * (size_t)P.k_ext[k]; };
   auto tile_b_elems = [&](int k, int j) { return (size_t)P.k_ext[k] * (size_t)P.n_ext[j]; };
@@ -444,23 +490,67 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   auto tile_a_elems = [&](int i, int k) { return (size_t)P.m_ext[i] * (size_t)P.k_ext[k]; };
   auto tile_b_elems = [&](int k, int j) { return (size_t)P.k_ext[k] * (size_t)P.n_ext[j]; };
 
-  // ---- resources
+  // ---- up-front validation: every tile this rank must supply exists (nothing may fail for a local reason once
+  //      the first collective has been enqueued: the peers would wait for this rank forever)
+  int local_rc = TADEV_OK;
+  for (int b = 0; b < nb && !local_rc; ++b)
+    for (const BlockStep& bs : bsteps[b]) {
+      const int k = bs.st->k;
+      if ((bs.bcast_a || bs.compute) && c == k % Pc)
+        for (int i : bs.a_rows)
+          if (!P.a_tiles[(size_t)i * Kt + k]) { tadev_set_error("tadev_summa_f64: A tile (%d,%d) is owned by this rank but has no data", i, k); local_rc = TADEV_EINVAL; }
+      if ((bs.bcast_b || bs.compute) && r == k % Pr)
+        for (int j : bs.st->b_cols)
+          if (!P.b_tiles[(size_t)k * Nt + j]) { tadev_set_error("tadev_summa_f64: B tile (%d,%d) is owned by this rank but has no data", k, j); local_rc = TADEV_EINVAL; }
+      if (bs.compute)
+        for (int64_t pp = bs.st->pair_begin; pp < bs.st->pair_end; ++pp)
+          if (!P.c_tiles[(size_t)S.pair_i[pp] * Nt + S.pair_j[pp]]) {
+            tadev_set_error("tadev_summa_f64: result tile (%d,%d) is non-zero and local but has no storage", S.pair_i[pp], S.pair_j[pp]);
+            local_rc = TADEV_EINVAL;
+          }
+      if (local_rc) break;
+    }
+
+  // ---- resources: events and device buffers are owned by `R`; its destructor releases them on EVERY exit path
+  //      (on an error path it first drains the four streams so that nothing still reads a buffer being freed)
+  struct Resources {
+    tadev_ctx* ctx; cudaStream_t s0, sc, sh, sd;
+    std::vector<cudaEvent_t> events;
+    std::vector<void*> buffers;
+    bool ok = false;
+    int event(cudaEvent_t* e, unsigned flags) {
+      TADEV_CHECK_CUDA(cudaEventCreateWithFlags(e, flags));
+      events.push_back(*e);
+      return TADEV_OK;
+    }
+    int alloc(size_t bytes, double** p) {
+      int rc = tadev_alloc(ctx, bytes, (void**)p, (tadev_stream)s0);
+      if (!rc && *p) buffers.push_back(*p);
+      return rc;
+    }
+    ~Resources() {
+      if (!ok) { for (cudaStream_t st : {s0, sc, sh, sd}) cudaStreamSynchronize(st); cudaGetLastError(); }
+      for (void* b : buffers) tadev_free(ctx, b, (tadev_stream)s0);
+      for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+  } R{ctx, s0, sc, sh, sd};
   cudaEvent_t ev_start, ev_end, ev_aux;
-  TADEV_CHECK_CUDA(cudaEventCreate(&ev_start));
-  TADEV_CHECK_CUDA(cudaEventCreate(&ev_end));
-  TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&ev_aux, cudaEventDisableTiming));
+  int rc0 = R.event(&ev_start, cudaEventDefault);
+  if (!rc0) rc0 = R.event(&ev_end, cudaEventDefault);
+  if (!rc0) rc0 = R.event(&ev_aux, cudaEventDisableTiming);
+  if (rc0) return rc0;
   const bool need_ring = max_bytes > 0;
   std::vector<double*> ring(D, nullptr);
   std::vector<cudaEvent_t> panel_ready(D), buf_free(D), h2d_done(D);
   std::vector<char> buf_used(D, 0);
-  for (int d = 0; d < D; ++d) {
-    if (need_ring) { int rc = tadev_alloc(ctx, max_bytes, (void**)&ring[d], s0); if (rc) return rc; }
-    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&panel_ready[d], cudaEventDisableTiming));
-    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&buf_free[d], cudaEventDisableTiming));
-    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&h2d_done[d], cudaEventDisableTiming));
+  for (int d = 0; d < D && !local_rc; ++d) {
+    if (need_ring) local_rc = R.alloc(max_bytes, &ring[d]);
+    if (!local_rc) local_rc = R.event(&panel_ready[d], cudaEventDisableTiming);
+    if (!local_rc) local_rc = R.event(&buf_free[d], cudaEventDisableTiming);
+    if (!local_rc) local_rc = R.event(&h2d_done[d], cudaEventDisableTiming);
   }
   double* bcache = nullptr;
-  if (b_cache && b_cache_elems) { int rc = tadev_alloc(ctx, b_cache_elems * 8, (void**)&bcache, s0); if (rc) return rc; }
+  if (!local_rc && b_cache && b_cache_elems) local_rc = R.alloc(b_cache_elems * 8, &bcache);
   // result blocks staged on the device when the result lives in host memory (double buffered)
   std::vector<size_t> cblock_elems(nb, 0);
   auto c_local = [&](int i, int j) {
@@ -478,11 +568,36 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   double* carena[2] = {nullptr, nullptr};
   cudaEvent_t c_done[2], d2h_done[2];
   bool c_used[2] = {false, false};
-  for (int x = 0; x < 2; ++x) {
-    if (c_host && cmax) { int rc = tadev_alloc(ctx, cmax * 8, (void**)&carena[x], s0); if (rc) return rc; }
-    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&c_done[x], cudaEventDisableTiming));
-    TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&d2h_done[x], cudaEventDisableTiming));
+  for (int x = 0; x < 2 && !local_rc; ++x) {
+    if (c_host && cmax) local_rc = R.alloc(cmax * 8, &carena[x]);
+    if (!local_rc) local_rc = R.event(&c_done[x], cudaEventDisableTiming);
+    if (!local_rc) local_rc = R.event(&d2h_done[x], cudaEventDisableTiming);
   }
+  // ---- agree on success across the grid before the first panel broadcast: a rank that failed validation or an
+  //      allocation returns its error and every other rank returns TADEV_ENCCL instead of blocking in NCCL
+  if (multi) {
+    int32_t* flag = nullptr;
+    if (cudaMallocHost((void**)&flag, sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); flag = nullptr; }
+    double* dflag = nullptr;
+    int arc = flag ? R.alloc(16, &dflag) : TADEV_ENOMEM;
+    if (!arc) {
+      *flag = local_rc;
+      TADEV_CHECK_CUDA(cudaMemcpyAsync(dflag, flag, sizeof(int32_t), cudaMemcpyHostToDevice, sc));
+      // every rank of the grid is in one row and one column communicator: max over both = max over the grid
+      ncclResult_t n1 = ncclAllReduce(dflag, dflag, 1, ncclInt32, ncclMax, ctx->row_comm, sc);
+      ncclResult_t n2 = n1 == ncclSuccess ? ncclAllReduce(dflag, dflag, 1, ncclInt32, ncclMax, ctx->col_comm, sc) : n1;
+      if (n2 != ncclSuccess) { cudaFreeHost(flag); tadev_set_error("tadev_summa_f64: status all-reduce failed: %s", ncclGetErrorString(n2)); return TADEV_ENCCL; }
+      TADEV_CHECK_CUDA(cudaMemcpyAsync(flag, dflag, sizeof(int32_t), cudaMemcpyDeviceToHost, sc));
+      TADEV_CHECK_CUDA(cudaStreamSynchronize(sc));
+      const int32_t grid_rc = *flag;
+      cudaFreeHost(flag);
+      if (local_rc) return local_rc;
+      if (grid_rc) { tadev_set_error("tadev_summa_f64: another rank of the process grid failed before the first broadcast (status %d)", grid_rc); return TADEV_ENCCL; }
+    } else {
+      if (flag) cudaFreeHost(flag);
+      return local_rc ? local_rc : arc;
+    }
+  } else if (local_rc) return local_rc;
   TADEV_CHECK_CUDA(cudaEventRecord(ev_start, s0));
   TADEV_CHECK_CUDA(cudaStreamWaitEvent(sc, ev_start, 0));
   TADEV_CHECK_CUDA(cudaStreamWaitEvent(sh, ev_start, 0));
@@ -505,10 +620,11 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   auto mark = [&](const char* what, int blk, int win, cudaStream_t st) {
     if (!trace) return;
     cudaEvent_t e;
-    if (cudaEventCreate(&e) != cudaSuccess) return;
+    if (R.event(&e, cudaEventDefault) != TADEV_OK) return;
     cudaEventRecord(e, st);
     marks.push_back({what, blk, win, e});
   };
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;  // around every GEMM launch (stats->gemm_ms)
   std::vector<char> touched((size_t)Mt * Nt, 0);
   int64_t npairs = 0, nlaunches = 0, bcast_bytes = 0, h2d_bytes = 0, d2h_bytes = 0, lazy_tiles = 0;
   double flops = 0.0;
@@ -703,6 +819,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
         }
       }
       if (any_bcast || ring_touched) {  // D2D packs also run on sc
+        mark("bcast_done", b, wi, sc);
         TADEV_CHECK_CUDA(cudaEventRecord(panel_ready[d], sc));
         TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, panel_ready[d], 0));
       }
@@ -742,8 +859,15 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
           tasks.push_back({contrib[n].A, contrib[n].B, contrib[n].k, 0});
         }
         groups.back().task_end = (int32_t)tasks.size();
+        GemmTimingHook& hook = tadev_gemm_timing_hook();
+        cudaEvent_t g0 = nullptr, g1 = nullptr;
+        if (R.event(&g0, cudaEventDefault) == TADEV_OK && R.event(&g1, cudaEventDefault) == TADEV_OK) {
+          hook.before = g0; hook.after = g1;
+          gemm_events.push_back({g0, g1});
+        }
         int rc = tadev_gemm_grouped_f64(ctx, s0, P.opA, P.opB, P.alpha, groups.data(), (int)groups.size(), tasks.data(),
                                         (int)tasks.size());
+        hook.before = hook.after = nullptr;
         if (rc) return rc;
         ++nlaunches;
         mark("gemm_done", b, wi, s0);
@@ -788,20 +912,21 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, ev_aux, 0));
   }
   TADEV_CHECK_CUDA(cudaEventRecord(ev_end, s0));
-  for (int d = 0; d < D; ++d) if (ring[d]) { int rc = tadev_free(ctx, ring[d], s0); if (rc) return rc; }
-  if (bcache) { int rc = tadev_free(ctx, bcache, s0); if (rc) return rc; }
-  for (int x = 0; x < 2; ++x) if (carena[x]) { int rc = tadev_free(ctx, carena[x], s0); if (rc) return rc; }
   TADEV_CHECK_CUDA(cudaEventSynchronize(ev_end));
   TADEV_CHECK_CUDA(cudaGetLastError());
-  float ms = 0;
+  float ms = 0, gemm_ms = 0;
   TADEV_CHECK_CUDA(cudaEventElapsedTime(&ms, ev_start, ev_end));
+  for (auto& ge : gemm_events) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, ge.first, ge.second) == cudaSuccess) gemm_ms += t; else cudaGetLastError();
+  }
   for (auto& mk : marks) {
     float t = 0;
     cudaEventSynchronize(mk.ev);
     cudaEventElapsedTime(&t, ev_start, mk.ev);
     fprintf(stderr, "[tadev summa rank %d] %-9s block %d window %2d  t=%9.3f ms\n", ctx->rank, mk.what, mk.block, mk.window, t);
-    cudaEventDestroy(mk.ev);
   }
+  R.ok = true;  // all streams were joined on s0 and s0 has drained: plain stream-ordered release
   if (stats) {
     stats->nsteps = (int64_t)S.steps.size();
     stats->nsteps_skipped = S.nskipped;
@@ -814,9 +939,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     stats->d2h_bytes = d2h_bytes;
     stats->row_blocks = nb;
     stats->lazy_tiles = lazy_tiles;
+    stats->gemm_ms = gemm_ms;
   }
-  cudaEventDestroy(ev_start); cudaEventDestroy(ev_end); cudaEventDestroy(ev_aux);
-  for (int d = 0; d < D; ++d) { cudaEventDestroy(panel_ready[d]); cudaEventDestroy(buf_free[d]); cudaEventDestroy(h2d_done[d]); }
-  for (int x = 0; x < 2; ++x) { cudaEventDestroy(c_done[x]); cudaEventDestroy(d2h_done[x]); }
   return TADEV_OK;
 }

@@ -284,6 +284,15 @@ class Device:
                 x.free()
         return out, nz
 
+    def allreduce_max_f32(self, x: np.ndarray) -> np.ndarray:
+        """Element-wise max over all ranks through the library's NCCL world communicator (shape replication)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        d = self.upload(x.ravel())
+        check(self.lib.tadev_shape_allreduce_max_f32(self.ctx, self.stream, d.ptr, x.size))
+        out = self.download(d, np.float32, x.shape)
+        d.free()
+        return out
+
     def build_pairlist(self, k: int, Pr: int, Pc: int, r: int, c: int, a: Optional[np.ndarray],
                        b: Optional[np.ndarray], cn: Optional[np.ndarray], Mt: int, Nt: int, Kt: int, threshold: float):
         d_a = self.upload(np.ascontiguousarray(a, dtype=np.float32).ravel()) if a is not None else None

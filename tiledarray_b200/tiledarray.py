@@ -478,13 +478,7 @@ class DistArray:
             return self
         norms = self.tile_norms().astype(f32)
         if self.world.size > 1:  # shapes are replicated: every rank needs every tile's norm (gop.max, sparse_shape.h:416)
-            import torch
-            import torch.distributed as dist
-            t = torch.from_numpy(norms.copy())
-            if dist.get_backend() == "nccl":
-                t = t.cuda()
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            norms = t.cpu().numpy()
+            norms = self.world.dev.allreduce_max_f32(norms)
         new_shape = SparseShape(self.world, norms, self.trange)
         for o in [o for o in self.tiles if new_shape.is_zero(o)]:
             del self.tiles[o]  # views into the arena: the memory is reclaimed with the arena
@@ -492,6 +486,9 @@ class DistArray:
         return self
 
     def release(self) -> None:
+        for x in getattr(self, "_extra_arenas", []):
+            x.free()
+        self._extra_arenas = []
         if self._arena is not None:
             self._arena.free()
             self._arena = None
@@ -519,6 +516,14 @@ _ASSIGNED = object()
 
 class Expr:
     factor = 1.0
+    mask = None  # result-shape override (Expr::set_shape, expressions/expr.h:116)
+
+    def set_shape(self, shape: "SparseShape"):
+        """``(a("m,k") * b("k,n")).set_shape(mask)``: the result shape is masked by ``mask``
+        (ContEngine::init_struct, cont_engine.h:526-528 -> SparseShape::mask, sparse_shape.h:653-676)."""
+        _ta_assert(isinstance(shape, SparseShape), "set_shape: a SparseShape is required")
+        self.mask = shape
+        return self
 
     def __mul__(self, other):
         if isinstance(other, (int, float)):
@@ -550,7 +555,9 @@ class TsrExpr(Expr):
         return _ASSIGNED
 
     def assign(self, expr, accumulate: bool = False) -> None:
+        outer_mask = expr.mask
         factor, expr = _peel(expr)
+        mask = expr.mask if expr.mask is not None else outer_mask
         if isinstance(expr, MultExpr):
             fl, left = _peel(expr.left)
             fr, right = _peel(expr.right)
@@ -560,11 +567,13 @@ class TsrExpr(Expr):
             if set(left.indices) == set(right.indices) == set(self.indices):
                 # every index is shared and kept: Hadamard product (mult_engine.h), no contraction
                 _ta_assert(not accumulate, "+= of a Hadamard product is not implemented")
+                _ta_assert(mask is None, "set_shape is implemented for contractions only")
                 ElementwiseEngine(self, _lib.EW_MULT, factor, left, 1.0, right).eval()
             else:
-                ContEngine(self, left, right, factor, accumulate).eval()
+                ContEngine(self, left, right, factor, accumulate, mask).eval()
             return
         _ta_assert(not accumulate, "+= is implemented for contractions only")
+        _ta_assert(mask is None, "set_shape is implemented for contractions only")
         if isinstance(expr, AddExpr):
             fl, left = _peel(expr.left)
             fr, right = _peel(expr.right)
@@ -615,6 +624,8 @@ class ContractionStats:
     d2h_bytes: int = 0
     row_blocks: int = 1
     lazy_tiles: int = 0
+    gemm_ms: float = 0.0
+    list_ms: float = 0.0
     swapped: bool = False
 
 
@@ -719,8 +730,10 @@ class ContEngine:
     stream_permutes = "auto"  # True/False/"auto": permute argument tiles just in time per SUMMA window
     stream_permute_bytes = 8 << 30  # "auto": stream when the permuted copy would exceed this many bytes
 
-    def __init__(self, result: TsrExpr, left: TsrExpr, right: TsrExpr, factor: float, accumulate: bool = False):
+    def __init__(self, result: TsrExpr, left: TsrExpr, right: TsrExpr, factor: float, accumulate: bool = False,
+                 mask: Optional[SparseShape] = None):
         self.result, self.left, self.right, self.factor, self.accumulate = result, left, right, factor, accumulate
+        self.mask = mask
         self.world = left.array.world
         self.dev = self.world.dev
 
@@ -781,6 +794,11 @@ class ContEngine:
         opt.stream_permute_bytes = ContEngine.stream_permute_bytes
         opt.depth, opt.steps_per_launch, opt.row_blocks = ContEngine.depth, ContEngine.steps_per_launch, ContEngine.row_blocks
         opt.threshold = SparseShape._threshold
+        if self.mask is not None:
+            mask_norms = np.ascontiguousarray(self.mask.norms, dtype=f32)
+            keep.append(mask_norms)
+            opt.mask_norms = mask_norms.ctypes.data_as(C.POINTER(C.c_float))
+            opt.mask_threshold = self.mask.my_threshold
         handle = C.c_void_p()
         rc = lib.tadev_contraction_create(dev.ctx, ",".join(self.result.indices).encode(), ",".join(self.left.indices).encode(),
                                           ",".join(self.right.indices).encode(), C.byref(dA), C.byref(dB), self.factor,
@@ -815,28 +833,51 @@ class ContEngine:
         # result arena
         c_on_host = Cres.memory == "host"
         need_bytes = int(info.arena_elems) * 8
-        if self.accumulate:
-            _ta_assert(old_result.trange == tr_target and old_result._arena is not None and old_result._arena.nbytes >= need_bytes
-                       and sorted(old_result.tiles) == sorted(ords.tolist()),
-                       "c += a*b: the existing result must have the tiling and tile set of the product")
-            arena = old_result._arena
-        elif c_on_host:
-            if old_host_arena is not None and old_host_arena.nbytes >= need_bytes:
-                arena = old_host_arena
-            else:
-                if old_host_arena is not None:
-                    old_host_arena.free()
-                arena = HostBuffer(need_bytes)
-        else:
-            arena = dev.alloc(need_bytes)
         st = _lib.ContractStatsC()
-        check(lib.tadev_contraction_eval(handle, arena.ptr, _lib.MEM_HOST if c_on_host else _lib.MEM_DEVICE,
-                                         int(self.accumulate), C.byref(st)))
+        mem_c = _lib.MEM_HOST if c_on_host else _lib.MEM_DEVICE
+        if self.accumulate:
+            # c += a*b: the product is added into the EXISTING tiles through their own pointers (any arena layout).
+            # Product tiles that are zero in c so far are created (zero-filled) first: the result shape is the sum
+            # of the two shapes (AddEngine semantics, SparseShape::add).
+            _ta_assert(old_result.trange == tr_target, "c += a*b: the existing result must have the tiling of the product")
+            _ta_assert(old_result.memory == Cres.memory and old_result.memory != "lazy", "c += a*b: bad result memory")
+            old_result._allocate()
+            missing = [(o_, e_) for o_, e_ in zip(ords.tolist(), elems.tolist()) if o_ not in old_result.tiles]
+            if missing:
+                _ta_assert(not old_result.shape.is_dense(), "c += a*b: a dense result is missing tiles")
+                tot = sum((e_ + 1) & ~1 for _, e_ in missing)
+                extra = HostBuffer(tot * 8) if c_on_host else dev.alloc(tot * 8)
+                if c_on_host:
+                    extra.numpy(np.float64, (tot,))[:] = 0.0
+                else:
+                    dev.memset(extra, 0)
+                old_result._extra_arenas = getattr(old_result, "_extra_arenas", []) + [extra]
+                off = 0
+                for o_, e_ in missing:
+                    old_result.tiles[o_] = extra.view(off * 8, e_ * 8)
+                    off += (e_ + 1) & ~1
+            table = (C.c_void_p * max(nloc, 1))(*[old_result.tiles[o_].ptr for o_ in ords.tolist()])
+            check(lib.tadev_contraction_eval_tiles(handle, table, mem_c, 1, C.byref(st)))
+            if not old_result.shape.is_dense():
+                old_result.shape = old_result.shape.add(new_shape)
+            arena = None
+        else:
+            if c_on_host:
+                if old_host_arena is not None and old_host_arena.nbytes >= need_bytes:
+                    arena = old_host_arena
+                else:
+                    if old_host_arena is not None:
+                        old_host_arena.free()
+                    arena = HostBuffer(need_bytes)
+            else:
+                arena = dev.alloc(need_bytes)
+            check(lib.tadev_contraction_eval(handle, arena.ptr, mem_c, 0, C.byref(st)))
         stats = ContractionStats()
         sm = st.summa
         stats.nsteps, stats.nsteps_skipped, stats.npairs = sm.nsteps, sm.nsteps_skipped, sm.npairs
         stats.nlaunches, stats.flops, stats.bcast_bytes, stats.device_ms = sm.nlaunches, sm.flops, sm.bcast_bytes, sm.device_ms
         stats.h2d_bytes, stats.d2h_bytes, stats.row_blocks, stats.lazy_tiles = sm.h2d_bytes, sm.d2h_bytes, sm.row_blocks, sm.lazy_tiles
+        stats.gemm_ms, stats.list_ms = sm.gemm_ms, sm.list_ms
         stats.permute_ms = st.permute_ms
         stats.swapped = bool(info.swapped)
 
@@ -873,3 +914,55 @@ def summa_arrays(world: World, trA: TiledRange, trB: TiledRange, shapeA=None, sh
     memB = "lazy" if lazy_seeds[1] is not None else memory
     return (DistArray(world, trA, shapeA, ownA, orderA, memA, lazy_seeds[0]),
             DistArray(world, trB, shapeB, ownB, orderB, memB, lazy_seeds[1]))
+
+
+def contraction_layout(world_size: int, target: str, lidx: str, trL: TiledRange, ridx: str, trR: TiledRange,
+                       exchange_operands: Optional[bool] = None):
+    """[host] tadev_contraction_layout: the ProcGrid and, per tile of each operand, its position in the fused
+    GEMM-side tile grid (-> owner rank and panel-contiguous arena order). Needs no device."""
+    lib = _lib.load()
+    keep: list = []
+
+    def desc(tr):
+        d = _lib.ArrayDescC()
+        bounds = np.asarray([b for dim in tr.dims for b in dim.bounds], dtype=np.int64)
+        ntiles = np.asarray([dim.ntiles for dim in tr.dims], dtype=np.int32)
+        keep.extend([bounds, ntiles])
+        d.rank, d.memory = tr.rank, _lib.MEM_DEVICE
+        d.bounds = bounds.ctypes.data_as(C.POINTER(C.c_int64))
+        d.ntiles = ntiles.ctypes.data_as(C.POINTER(C.c_int32))
+        return d
+
+    dL, dR = desc(trL), desc(trR)
+    opt = _lib.ContractOptionsC()
+    check(lib.tadev_contract_options_default(C.byref(opt)))
+    opt.exchange_operands = int(ContEngine.exchange_operands if exchange_operands is None else exchange_operands)
+    info = _lib.LayoutInfoC()
+    lr, lc = np.zeros(max(trL.ntiles, 1), np.int32), np.zeros(max(trL.ntiles, 1), np.int32)
+    rr, rc_ = np.zeros(max(trR.ntiles, 1), np.int32), np.zeros(max(trR.ntiles, 1), np.int32)
+    rc = lib.tadev_contraction_layout(target.encode(), lidx.encode(), ridx.encode(), C.byref(dL), C.byref(dR), C.byref(opt),
+                                      world_size, C.byref(info), lr.ctypes.data, lc.ctypes.data, rr.ctypes.data, rc_.ctypes.data)
+    if rc == _lib.EINVAL:
+        raise TiledArrayException(lib.tadev_last_error().decode())
+    check(rc)
+    return info, (lr, lc), (rr, rc_)
+
+
+def contraction_arrays(world: World, target: str, lidx: str, trL: TiledRange, ridx: str, trR: TiledRange,
+                       shapeL=None, shapeR=None, memory=("device", "device"), lazy_seeds=(None, None)):
+    """Create the two operands of ``c(target) = a(lidx) * b(ridx)`` already distributed the way SUMMA wants them
+    (cyclic maps of the ProcGrid over the fused tile grids, proc_grid.h:566-597) with panel-contiguous arenas, for any
+    index lists (permuted / transposed operands, exchanged operands). Returns (a, b, (Pr, Pc)); the caller then
+    calls ``world.init_comm(Pr, Pc)``. The analogue of constructing TA::DistArrays on the pmaps ContEngine would pick."""
+    info, (lr, lc), (rr, rc_) = contraction_layout(world.size, target, lidx, trL, ridx, trR)
+    Pr, Pc = info.Pr, info.Pc
+    out = []
+    for tr, shape, fr, fc, role, mem, seed in ((trL, shapeL, lr, lc, info.left_role, memory[0], lazy_seeds[0]),
+                                               (trR, shapeR, rr, rc_, info.right_role, memory[1], lazy_seeds[1])):
+        owners = ((fr.astype(np.int64) % Pr) * Pc + fc.astype(np.int64) % Pc).tolist()
+        # role 0 (A(i,k)): column panels contiguous -> order by (k = fcol, i = frow); role 1 (B(k,j)): by (k = frow, j = fcol)
+        key = fc.astype(np.int64) * (int(fr.max()) + 1) + fr if role == 0 else fr.astype(np.int64) * (int(fc.max()) + 1) + fc
+        order = np.argsort(key, kind="stable").tolist()
+        mem = "lazy" if seed is not None else mem
+        out.append(DistArray(world, tr, shape, (lambda o, ow=owners: ow[o]), order, mem, seed))
+    return out[0], out[1], (Pr, Pc)
