@@ -272,12 +272,15 @@ def main():
     peak_tf = max(dev.probe_fp64_peak(0, 40000)[0] for _ in range(2))
     peak_sustained = dev.probe_fp64_peak(0, 400000)[0]
 
-    for _ in range(warmup):
-        wl.step()
-    barrier()
+    # the sampler (nvidia-smi -lms 200) is started BEFORE the warm-up steps: its start-up (NVML initialisation takes
+    # driver locks for tens of ms and stalled a CUDA call of the first timed step when it was started after them) then
+    # falls into the warm-up; it keeps sampling every 200 ms throughout the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(warmup):
+        wl.step()
+    barrier()
     launches0 = dev.launch_count()
     kernel_ms, gemm_ms, step_stats = [], [], None
     with dev.timer() as tm:  # CUDA events on the stream the driver launches on

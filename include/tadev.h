@@ -65,6 +65,19 @@ int tadev_event_create(tadev_ctx* ctx, void** ev);
 int tadev_event_record(tadev_ctx* ctx, void* ev, tadev_stream s);
 int tadev_event_elapsed_ms(tadev_ctx* ctx, void* ev_start, void* ev_stop, float* ms); /* syncs on ev_stop */
 int tadev_event_destroy(tadev_ctx* ctx, void* ev);
+/* Asynchronous completion and cross-stream ordering (the tile plug-in's contract: a tile op enqueues work and
+ * returns; the caller's runtime completes its task from a host function on the stream - external/device.h:847-875
+ * sync_madness_task_with + madness::add_device_task, reduce_task.h:460-486 - and orders dependent work on other
+ * streams with events instead of host synchronisation). Sync events have timing disabled (cheap to record). */
+int tadev_sync_event_create(tadev_ctx* ctx, void** ev);
+int tadev_stream_wait_event(tadev_ctx* ctx, tadev_stream s, void* ev); /* work enqueued on s later waits for ev */
+int tadev_event_query(tadev_ctx* ctx, void* ev, int* done);           /* non-blocking */
+int tadev_event_sync(tadev_ctx* ctx, void* ev);                       /* blocks the calling host thread */
+typedef void (*tadev_host_fn)(void* user);
+/* fn(user) runs on a runtime thread once everything enqueued on s so far has finished (cudaLaunchHostFunc); it
+ * must not call CUDA / tadev functions. This is the hook a MADNESS device task completes from. */
+int tadev_stream_add_callback(tadev_ctx* ctx, tadev_stream s, tadev_host_fn fn, void* user);
+int tadev_memcpy_d2d(tadev_ctx* ctx, void* d_dst, const void* d_src, size_t bytes, tadev_stream s);
 int tadev_host_alloc(size_t bytes, void** h_ptr); /* pinned */
 int tadev_host_free(void* h_ptr);
 
@@ -105,8 +118,9 @@ typedef struct {
 int tadev_gemm_grouped_f64(tadev_ctx* ctx, tadev_stream s, int opA, int opB, double alpha,
                            const tadev_gemm_group* h_groups, int ngroups,
                            const tadev_gemm_task* h_tasks, int ntasks);
-/* Same, but descriptors already live in device memory (used by the SUMMA driver, whose
- * per-step lists are produced on the device by tadev_build_pairlist). */
+/* Same, but descriptors already live in device memory (generic cp.async kernel; d_tile_prefix[g] = first
+ * 128x128 work item of group g, ngroups + 1 entries). The SUMMA driver feeds the GEMM kernels with lists its
+ * own device kernels build per window (csrc/tilelist.cu, see tadev_build_tile_lists). */
 int tadev_gemm_grouped_f64_dev(tadev_ctx* ctx, tadev_stream s, int opA, int opB, double alpha,
                                const tadev_gemm_group* d_groups, int ngroups,
                                const tadev_gemm_task* d_tasks, const int32_t* d_tile_prefix,
@@ -134,10 +148,15 @@ int tadev_permute_batched(tadev_ctx* ctx, tadev_stream s, int rank, const int64_
  * device/btas_um_tensor.h:377-384 axpy). */
 int tadev_add_to_f64(tadev_ctx* ctx, tadev_stream s, size_t n, double* d_result, const double* d_arg);
 int tadev_scale_f64(tadev_ctx* ctx, tadev_stream s, size_t n, double* d_x, double factor);
-/* squared Frobenius norms of `ntiles` tiles (for truncate / true result shapes,
- * dist_array.h:1553). d_ptrs/d_sizes are device arrays; out is a device array of doubles. */
+/* squared Frobenius norms of `ntiles` (<= 65535) tiles (for truncate / true result shapes, dist_array.h:1553;
+ * Tensor::squared_norm, tile_interface.h). d_ptrs/d_sizes are device arrays; out is a device array of doubles;
+ * max_elems = host-known upper bound of the sizes (launch geometry). Deterministic: a tile's result depends only
+ * on its own data and size (fixed 16384-element chunks summed in ascending order). */
 int tadev_tile_sqnorms_f64(tadev_ctx* ctx, tadev_stream s, int ntiles, const double* const* d_ptrs,
-                           const int64_t* d_sizes, double* d_out);
+                           const int64_t* d_sizes, int64_t max_elems, double* d_out);
+/* squared Frobenius norm of ONE tile handed to the host (Tensor::squared_norm / norm of the tile interface):
+ * blocks until the reduction on s has finished. */
+int tadev_sqnorm_f64(tadev_ctx* ctx, tadev_stream s, size_t n, const double* d_x, double* h_out);
 /* Batched element-wise tile operations (tile_op/add.h, subt.h, scal.h, mult.h; GPU reference
  * device/btas_um_tensor.h:377-470 and device/kernel/thrust/mult_kernel.h): for every tile t
  *   TADEV_EW_AXPBY: out[t] = alpha * x[t] + beta * y[t]      (add, subt, scale, copy)
@@ -162,7 +181,8 @@ int tadev_fill_uniform_f64(tadev_ctx* ctx, tadev_stream s, double* d_x, size_t n
 int tadev_shape_scale_f32(tadev_ctx* ctx, tadev_stream s, float* d_norms, const float* d_left,
                           int64_t nleft, const float* d_right, int64_t nright, float threshold,
                           uint64_t* d_nzero);
-/* out[m,n] = |factor| * sum_k (a[m,k]*ksz[k]) * (b[k,n]*ksz[k]), sequential k, fp32 FMA;
+/* out[m,n] = |factor| * sum_k (a[m,k]*ksz[k]) * (b[k,n]*ksz[k]), sequential k, every fp32 multiply and add
+ * rounded separately (no FMA contraction: the oracle's fixed order, oracle/ta_oracle.py shape_gemm_kernel);
  * values < threshold are hard-zeroed and counted. Kt == 0: outer product a[m]*b[n]*|factor|. */
 int tadev_shape_gemm_f32(tadev_ctx* ctx, tadev_stream s, int Mt, int Nt, int Kt, const float* d_a,
                          const float* d_b, const float* d_ksz, float abs_factor, float threshold,
@@ -178,6 +198,17 @@ int tadev_shape_mask_f32(tadev_ctx* ctx, tadev_stream s, int64_t n, float* d_nor
 int tadev_build_pairlist(tadev_ctx* ctx, tadev_stream s, int k, int Pr, int Pc, int r, int c, int Mt,
                          int Nt, int Kt, const float* d_a, const float* d_b, const float* d_c,
                          float threshold, int32_t* d_pair_i, int32_t* d_pair_j, int32_t* d_npairs);
+
+/* The list kernel the SUMMA driver runs per window of steps (csrc/tilelist.cu), as a stand-alone entry: for the
+ * steps d_ksteps[0..nsteps) and every LOCAL result tile g = li * ncl + lj (i = r + li*Pr, j = c + lj*Pc; nrl x ncl
+ * local tiles, row-major) the chained contributions {k : a[i,k] >= thr, b[k,j] >= thr, c[i,j] >= thr} in step
+ * order: d_task_k[d_group_begin[g] .. d_group_begin[g+1]). Same predicate as Summa::contract
+ * (contraction_eval.h:1311-1384), regrouped per result tile (the ContractReduce chains the grouped GEMM executes).
+ * Multi-CTA; all arrays are device arrays; NULL norms = dense. *d_ntasks = total (also d_group_begin[nrl*ncl]). */
+int tadev_build_tile_lists(tadev_ctx* ctx, tadev_stream s, int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt,
+                           const int32_t* d_ksteps, int nsteps, const float* d_a, const float* d_b, const float* d_c,
+                           float threshold, int32_t* d_group_begin, int32_t* d_task_k, int64_t capacity,
+                           int32_t* d_ntasks);
 
 /* ---- [host] process grid / pmap / permutation planning ------------------------------------ */
 /* ProcGrid (proc_grid.h:97-260): grid dims + this rank's coordinates and local counts.

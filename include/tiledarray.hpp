@@ -534,7 +534,9 @@ class DistArray {
     check(tadev_alloc(ctx, n * 8, &d_p, st)); check(tadev_alloc(ctx, n * 8, &d_s, st)); check(tadev_alloc(ctx, n * 8, &d_o, st));
     check(tadev_memcpy_h2d(ctx, d_p, ptrs.data(), n * 8, st));
     check(tadev_memcpy_h2d(ctx, d_s, sizes.data(), n * 8, st));
-    check(tadev_tile_sqnorms_f64(ctx, st, (int)n, (const double* const*)d_p, (const int64_t*)d_s, (double*)d_o));
+    int64_t max_elems = 0;
+    for (int64_t e : sizes) max_elems = std::max(max_elems, e);
+    check(tadev_tile_sqnorms_f64(ctx, st, (int)n, (const double* const*)d_p, (const int64_t*)d_s, max_elems, (double*)d_o));
     std::vector<double> sq(n);
     check(tadev_memcpy_d2h(ctx, sq.data(), d_o, n * 8, st));
     check(tadev_stream_sync(ctx, st));

@@ -5,6 +5,9 @@
 //   contract_reduce.h:397-398                   add_to merge
 // Build: g++ -std=c++17 -I include tests/cpp/test_tile_plugin.cpp -L tiledarray_b200 -ltadev
 // Runs on a GPU box only (tests/test_gpu_cpp_plugin.py).
+#include <atomic>
+#include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <thread>
@@ -142,6 +145,108 @@ int main() {
     int nbad = 0;
     for (int b : bad) nbad += b;
     CHECK(nbad == 0);
+  }
+  // ---- asynchrony: chains of tile ops across streams with NO host synchronisation until the very end
+  // (external/device.h:847-875 contract). Every tile of a chain lives on a different stream (ordinal = step), so each
+  // op depends on the previous one through the event ordering of the plug-in; inputs are dropped while consumers
+  // are still queued (their storage must outlive the reads); completion is observed through callbacks.
+  {
+    const int nthreads = 6, nchains = 18, dim = 64, steps = 12;
+    const auto X = int_matrix(dim, dim, 11);
+    std::vector<double> I((size_t)dim * dim, 0.0);
+    for (int i = 0; i < dim; ++i) I[(size_t)i * dim + i] = 1.0;
+    Tile tI(ctx, {dim, dim}, 1);
+    tI.from_host(I.data());
+    std::atomic<int> callbacks{0};
+    std::vector<Tile> finals(nchains);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&, t] {
+        GemmHelper h(Op::NoTrans, Op::NoTrans, 2u, 2u, 2u);
+        for (int chain = t; chain < nchains; chain += nthreads) {
+          Tile cur(ctx, {dim, dim}, (uint64_t)chain);
+          cur.from_host(X.data());
+          for (int st = 0; st < steps; ++st) {
+            // alternate: transpose, multiply by the identity (on another stream), clone, add to itself and halve
+            Tile nxt;
+            tadev::this_task_ordinal() = (uint64_t)(chain + st);  // results of this step go to another stream
+            switch (st % 4) {
+              case 0: nxt = permute(cur, {1, 0}); break;
+              case 1: nxt = gemm(cur, tI, 1.0, h); break;
+              case 2: nxt = clone(cur); break;
+              default: nxt = add(cur, cur); scale_to(nxt, 0.5); break;
+            }
+            cur = nxt;  // the previous tile is released while its consumer may still be queued
+          }
+          tadev::this_task_ordinal() = 0;
+          cur.on_ready([](void* u) { static_cast<std::atomic<int>*>(u)->fetch_add(1); }, &callbacks);
+          finals[chain] = cur;
+        }
+      });
+    for (auto& th : pool) th.join();
+    // steps: 3 transposes in 12 steps (st = 0, 4, 8) -> odd number -> transposed once overall
+    int nbad = 0;
+    std::vector<double> got((size_t)dim * dim);
+    for (int chain = 0; chain < nchains; ++chain) {
+      finals[chain].to_host(got.data());
+      for (int i = 0; i < dim; ++i) for (int j = 0; j < dim; ++j) if (got[(size_t)j * dim + i] != X[(size_t)i * dim + j]) ++nbad;
+    }
+    CHECK(nbad == 0);
+    ctx.sync();
+    CHECK(callbacks.load() == nchains);
+  }
+  // squared_norm / norm / shift / subt / mult
+  {
+    const int dim = 300;  // > one 16384-element reduction chunk
+    const auto X = int_matrix(dim, dim, 21);
+    Tile tx(ctx, {dim, dim});
+    tx.from_host(X.data());
+    double want = 0;
+    for (double v : X) want += v * v;
+    CHECK(squared_norm(tx) == want);
+    CHECK(norm(tx) == std::sqrt(want));
+    Tile sh = shift(tx, {5, -2});
+    CHECK((sh.lobound() == tadev::Range{5, -2}) && (tx.lobound() == tadev::Range{0, 0}));
+    Tile d = subt(sh, tx);
+    CHECK(squared_norm(d) == 0.0);
+    Tile p = mult(tx, tx);
+    std::vector<double> got(X.size());
+    p.to_host(got.data());
+    bool ok = true;
+    for (size_t i = 0; i < X.size(); ++i) ok = ok && got[i] == X[i] * X[i];
+    CHECK(ok);
+  }
+  // per-tile permute throughput (the path a TA::Tile permute takes, one launch per tile): 8 MiB tiles
+  // (16,16,64,64) -> (0,2,3,1), no host sync between launches; algorithmic bytes = 2 x tile bytes
+  {
+    const tadev::Range ext{16, 16, 64, 64};
+    const int ntiles = 64, reps = 6;
+    std::vector<Tile> src;
+    for (int i = 0; i < ntiles; ++i) { src.emplace_back(ctx, ext, (uint64_t)i); tadev_fill_uniform_f64(ctx.get(), src.back().stream(), src.back().data(), (size_t)src.back().size(), 5, (uint64_t)i << 32); src.back().release_write(); }
+    ctx.sync();
+    {  // warm-up: grow the tile pool (mapping fresh device memory costs ~100 us per tile, once)
+      std::vector<Tile> warm;
+      for (int i = 0; i < ntiles; ++i) warm.push_back(permute(src[i], {0, 2, 3, 1}));
+      ctx.sync();
+    }
+    for (int nthr : {1, 3}) {
+      std::vector<std::vector<Tile>> keep(nthr);
+      ctx.sync();
+      const auto t0 = std::chrono::steady_clock::now();
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nthr; ++t)
+        pool.emplace_back([&, t] {
+          for (int rp = 0; rp < reps; ++rp) {
+            keep[t].clear();  // results of the previous round go back to the pool (stream-ordered)
+            for (int i = t; i < ntiles; i += nthr) keep[t].push_back(permute(src[i], {0, 2, 3, 1}));
+          }
+        });
+      for (auto& th : pool) th.join();
+      ctx.sync();
+      const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      const double gbs = 2.0 * 8.0 * 16 * 16 * 64 * 64 * ntiles * reps / secs / 1e9;
+      std::printf("PERMUTE_PER_TILE threads=%d tiles=%d x %d GBs=%.1f\n", nthr, ntiles, reps, gbs);
+    }
   }
   ctx.sync();
   std::printf(failures ? "CPP_PLUGIN FAILED (%d)\n" : "CPP_PLUGIN OK\n", failures);

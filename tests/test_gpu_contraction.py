@@ -631,3 +631,42 @@ def test_c3_shaped_every_tile(world):
     assert ContEngine.last_stats.flops == 2.0 * pairs * T ** 3
     for x in (a, b, c):
         x.release()
+
+
+@pytest.mark.parametrize("case", ["dense_ragged", "sparse", "permuted", "host"])
+def test_device_lists_match_host_lists(world, case, monkeypatch):
+    """The SUMMA driver's device-built tile lists (default) and the host-built lists (TADEV_HOST_LISTS=1) must give
+    the same launches: identical results bit for bit, identical pair counts and flop counts."""
+    rng = np.random.default_rng(23)
+    if case == "dense_ragged":
+        d = TiledRange1(*KA.FIXTURE_BOUNDS)
+        a, _ = _dense_array(world, _tr(d, d), rng)
+        b, _ = _dense_array(world, _tr(d, d), rng)
+        args = ("m,n", "m,k", "k,n", _tr(d, d))
+    elif case == "sparse":
+        dm, dk, dn = _uniform(96, 16), _uniform(128, 16), _uniform(80, 16)
+        (a, _, _), (b, _, _) = _sparse_pair(world, _tr(dm, dk), _tr(dk, dn), 0.4, rng, integer=False)
+        args = ("m,n", "m,k", "k,n", _tr(dm, dn))
+    elif case == "permuted":
+        s, v = TiledRange1(0, 4, 8), TiledRange1(0, 16, 32, 40)
+        a, _ = _dense_array(world, _tr(s, s, v, v), rng)
+        b, _ = _dense_array(world, _tr(s, v, s, v), rng)
+        args = ("i,a,j,b", "i,k,a,c", "j,c,k,b", _tr(s, v, s, v))
+    else:
+        t = _uniform(256, 64)
+        full_a, full_b = rng.uniform(-1, 1, (256, 256)), rng.uniform(-1, 1, (256, 256))
+        a = DistArray(world, _tr(t, t), memory="host").init_from_numpy(full_a)
+        b = DistArray(world, _tr(t, t), memory="host").init_from_numpy(full_b)
+        args = ("m,n", "m,k", "k,n", _tr(t, t))
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TADEV_HOST_LISTS", mode)
+        c = DistArray(world, args[3], memory="host" if case == "host" else "device")
+        c[args[0]] = a[args[1]] * b[args[2]]
+        st = ContEngine.last_stats
+        out[mode] = (c.to_numpy(), st.npairs, st.flops, st.nlaunches, sorted(c.tiles))
+        c.release()
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert out["0"][1:] == out["1"][1:]
+    for x in (a, b):
+        x.release()

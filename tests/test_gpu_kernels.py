@@ -348,3 +348,37 @@ def test_pairlist_bit_exact(dev, grid):
                 for k in range(Kt):
                     pi, pj = dev.build_pairlist(k, Pr, Pc, r, c, an, bn, cnn, Mt, Nt, Kt, float(thr))
                     assert list(zip(pi.tolist(), pj.tolist())) == want.get(k, [])
+
+
+@pytest.mark.parametrize("grid", [(1, 1), (2, 2), (4, 2), (1, 8)])
+def test_window_tile_lists_bit_exact(dev, grid):
+    """tadev_build_tile_lists — the kernel the SUMMA driver runs per window (csrc/tilelist.cu) — against
+    Summa::contract restated (contraction_eval.h:1311-1384): for a window of steps, the pairs the oracle schedules
+    step by step, regrouped per local result tile in step order, must be EXACTLY the device's chains (every rank,
+    sparse with extra result zeros and dense, whole-contraction windows and partial windows)."""
+    rng = np.random.default_rng(17)
+    Mt, Nt, Kt = 37, 29, 11
+    thr = np.float32(0.5)
+    a = np.where(rng.random((Mt, Kt)) < 0.3, 1.0, 0.0).astype(np.float32)
+    b = np.where(rng.random((Kt, Nt)) < 0.3, 1.0, 0.0).astype(np.float32)
+    cn = ((a @ b) > 0).astype(np.float32)
+    cn[rng.random((Mt, Nt)) < 0.2] = 0
+    Pr, Pc = grid
+    for (an, bn, cnn) in ((a, b, cn), (None, None, None)):
+        for r in range(Pr):
+            for c in range(Pc):
+                sched = dict(O.summa_rank_schedule(Pr, Pc, r, c, Mt, Nt, Kt, None if an is None else an < thr,
+                                                   None if bn is None else bn < thr, None if cnn is None else cnn < thr))
+                for window in (list(range(Kt)), [2, 3, 4, 5], [7], []):
+                    chains = {}
+                    for k in window:
+                        for (i, j) in sched.get(k, []):
+                            chains.setdefault((i, j), []).append(k)
+                    gb, tk = dev.build_tile_lists(window, Pr, Pc, r, c, an, bn, cnn, Mt, Nt, Kt, float(thr))
+                    ncl = (Nt - c + Pc - 1) // Pc if c < Nt else 0
+                    nrl = (Mt - r + Pr - 1) // Pr if r < Mt else 0
+                    assert len(gb) == nrl * ncl + 1 and gb[-1] == len(tk) == sum(len(v) for v in chains.values())
+                    for li in range(nrl):
+                        for lj in range(ncl):
+                            g = li * ncl + lj
+                            assert tk[gb[g]:gb[g + 1]].tolist() == chains.get((r + li * Pr, c + lj * Pc), [])

@@ -130,6 +130,12 @@ PROTOTYPES = {
     "tadev_event_record": (_i, [_vp, _vp, _vp]),
     "tadev_event_elapsed_ms": (_i, [_vp, _vp, _vp, _P(_f)]),
     "tadev_event_destroy": (_i, [_vp, _vp]),
+    "tadev_sync_event_create": (_i, [_vp, _P(_vp)]),
+    "tadev_stream_wait_event": (_i, [_vp, _vp, _vp]),
+    "tadev_event_query": (_i, [_vp, _vp, _P(_i)]),
+    "tadev_event_sync": (_i, [_vp, _vp]),
+    "tadev_stream_add_callback": (_i, [_vp, _vp, _vp, _vp]),
+    "tadev_memcpy_d2d": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "tadev_host_alloc": (_i, [_sz, _P(_vp)]),
     "tadev_host_free": (_i, [_vp]),
     "tadev_gemm_grouped_f64": (_i, [_vp, _vp, _i, _i, _d, _P(GemmGroup), _i, _P(GemmTask), _i]),
@@ -139,13 +145,15 @@ PROTOTYPES = {
     "tadev_permute_batched": (_i, [_vp, _vp, _i, _P(_i64), _P(C.c_int32), _i, _i, _P(_vp), _P(_vp)]),
     "tadev_add_to_f64": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "tadev_scale_f64": (_i, [_vp, _vp, _sz, _vp, _d]),
-    "tadev_tile_sqnorms_f64": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "tadev_tile_sqnorms_f64": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp]),
+    "tadev_sqnorm_f64": (_i, [_vp, _vp, _sz, _vp, _P(_d)]),
     "tadev_tiles_binary_f64": (_i, [_vp, _vp, _i, _i, _P(_vp), _P(_vp), _P(_vp), _P(_i64), _d, _d]),
     "tadev_fill_uniform_f64": (_i, [_vp, _vp, _vp, _sz, _u64, _u64]),
     "tadev_shape_scale_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _f, _vp]),
     "tadev_shape_gemm_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp]),
     "tadev_shape_mask_f32": (_i, [_vp, _vp, _i64, _vp, _vp, _f, _f, _vp]),
     "tadev_build_pairlist": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "tadev_build_tile_lists": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _i64, _vp]),
     "tadev_proc_grid_make": (_i, [_i, _i, _i64, _i64, _i64, _i64, _P(ProcGridC)]),
     "tadev_cyclic_owner": (_i, [_i64, _i64, _i, _i, _P(_i)]),
     "tadev_plan_contraction": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, _P(ContractionPlanC)]),

@@ -108,6 +108,16 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
                                int ntasks, int total_cta_tiles);
 void tadev_tmap_cache_destroy(tadev_ctx* ctx);
 
+// device-side task of the fast (TMA) kernel: the public task + the tensor maps of its k-contiguous operands
+struct TadevWsTask {
+  const double* A;
+  const double* B;
+  int32_t k;
+  int32_t pad;
+  const void* mapA;  // CUtensorMap*
+  const void* mapB;
+};
+
 // Optional per-launch timing hook of the grouped GEMM: when set (by the SUMMA driver, on the calling thread) the
 // next launch records ev[0] immediately before and ev[1] immediately after the kernel on its stream, so the
 // kernel's own duration is measured without the descriptor upload / panel waits that precede it.

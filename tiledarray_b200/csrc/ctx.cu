@@ -178,6 +178,45 @@ extern "C" int tadev_event_destroy(tadev_ctx* ctx, void* ev) {
   return TADEV_OK;
 }
 
+// ---- asynchronous completion / cross-stream ordering for the tile plug-in --------------------------------------
+// (reference contract: tile ops enqueue work and return; the runtime completes the task from a host function on
+// the stream, external/device.h:847-875 sync_madness_task_with, madness::add_device_task; reduce_task.h:460-486)
+extern "C" int tadev_sync_event_create(tadev_ctx* ctx, void** ev) {
+  TADEV_REQUIRE(ctx && ev, "tadev_sync_event_create: null");
+  cudaEvent_t e;
+  TADEV_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *ev = (void*)e;
+  return TADEV_OK;
+}
+extern "C" int tadev_stream_wait_event(tadev_ctx* ctx, tadev_stream s, void* ev) {
+  TADEV_REQUIRE(ctx && ev, "tadev_stream_wait_event: null");
+  TADEV_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)ev, 0));
+  return TADEV_OK;
+}
+extern "C" int tadev_event_query(tadev_ctx* ctx, void* ev, int* done) {
+  TADEV_REQUIRE(ctx && ev && done, "tadev_event_query: null");
+  cudaError_t e = cudaEventQuery((cudaEvent_t)ev);
+  if (e == cudaErrorNotReady) { *done = 0; return TADEV_OK; }
+  TADEV_CHECK_CUDA(e);
+  *done = 1;
+  return TADEV_OK;
+}
+extern "C" int tadev_event_sync(tadev_ctx* ctx, void* ev) {
+  TADEV_REQUIRE(ctx && ev, "tadev_event_sync: null");
+  TADEV_CHECK_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
+  return TADEV_OK;
+}
+extern "C" int tadev_stream_add_callback(tadev_ctx* ctx, tadev_stream s, tadev_host_fn fn, void* user) {
+  TADEV_REQUIRE(ctx && fn, "tadev_stream_add_callback: null");
+  TADEV_CHECK_CUDA(cudaLaunchHostFunc((cudaStream_t)s, fn, user));
+  return TADEV_OK;
+}
+extern "C" int tadev_memcpy_d2d(tadev_ctx* ctx, void* d_dst, const void* d_src, size_t bytes, tadev_stream s) {
+  TADEV_REQUIRE(ctx, "tadev_memcpy_d2d: null ctx");
+  if (bytes) TADEV_CHECK_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+  return TADEV_OK;
+}
+
 extern "C" int tadev_launch_count(tadev_ctx* ctx, int64_t* n) {
   TADEV_REQUIRE(ctx && n, "tadev_launch_count: null");
   *n = ctx->launches.load();

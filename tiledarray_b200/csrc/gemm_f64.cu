@@ -108,6 +108,7 @@ gemm_grouped_f64_kernel(const tadev_gemm_group* __restrict__ groups, int ngroups
 
   // ---- locate my work item: binary search for the group that owns CTA tile blockIdx.x
   const int w = blockIdx.x;
+  if (w >= __ldg(tile_prefix + ngroups)) return;  // device-built lists launch an upper bound of CTAs (tilelist.cu)
   int lo = 0, hi = ngroups;  // invariant: prefix[lo] <= w < prefix[hi]
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;

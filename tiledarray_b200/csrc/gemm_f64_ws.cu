@@ -35,6 +35,7 @@
 #include <unordered_map>
 
 #include "common.h"
+#include "tilelist.h"
 
 namespace {
 
@@ -57,14 +58,7 @@ constexpr int STAGE_DOUBLES = SUB * SUBSTAGE_DOUBLES;
 constexpr int SMEM_DATA_BYTES = STAGES * SUB * 2 * SLAB_BYTES;  // 3 x 2 x 34816 = 208896
 constexpr int LAST_FLAG = 0x100;
 
-struct WsTask {  // device-side task: public task + tensor maps of its k-contiguous operands
-  const double* A;
-  const double* B;
-  int32_t k;
-  int32_t pad;
-  const CUtensorMap* mapA;
-  const CUtensorMap* mapB;
-};
+using WsTask = TadevWsTask;  // device-side task: public task + tensor maps of its k-contiguous operands
 
 struct Ctrl {  // lives after the data ring in dynamic smem
   unsigned long long full[STAGES];
@@ -125,7 +119,7 @@ template <int OPA, int OPB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngroups,
                            const WsTask* __restrict__ tasks, const int2* __restrict__ items,
-                           int total_tiles, int* __restrict__ tile_counter, double alpha, int static_sched,
+                           const int* __restrict__ total_ptr, int* __restrict__ tile_counter, double alpha, int static_sched,
                            int wave_sync) {
   constexpr bool A_KIN = (OPA == TADEV_OP_N);  // A stored [m][k]
   constexpr bool B_KIN = (OPB == TADEV_OP_T);  // B stored [n][k]
@@ -145,6 +139,9 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
     if (warp != NCONS) return;
     // =============================== producer warp ===============================
+    // number of work items: host-built lists stage it next to the scheduler counters, device-built lists
+    // (tilelist.cu) leave it in their counter block
+    const int total_tiles = __ldg(total_ptr);
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0;; ++it) {
@@ -199,8 +196,8 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
         const int K = T.k;
         if (K <= 0) continue;
         if (lane == 0) {
-          if (A_KIN) tensormap_acquire(T.mapA);
-          if (B_KIN) tensormap_acquire(T.mapB);
+          if (A_KIN) tensormap_acquire(static_cast<const CUtensorMap*>(T.mapA));
+          if (B_KIN) tensormap_acquire(static_cast<const CUtensorMap*>(T.mapB));
         }
         __syncwarp();
         for (int k0 = 0; k0 < K; k0 += BK * SUB) {
@@ -223,8 +220,8 @@ gemm_grouped_f64_ws_kernel(const tadev_gemm_group* __restrict__ groups, int ngro
             for (int sub = 0; sub < SUB; ++sub) {
               if (kb - sub * BK <= 0) break;
               double* sA = sStage + sub * SUBSTAGE_DOUBLES;
-              if (A_KIN) tma_2d_g2s(sA, T.mapA, k0 + sub * BK, m0, &ctrl->full[stage]);
-              if (B_KIN) tma_2d_g2s(sA + SLAB_DOUBLES, T.mapB, k0 + sub * BK, n0, &ctrl->full[stage]);
+              if (A_KIN) tma_2d_g2s(sA, static_cast<const CUtensorMap*>(T.mapA), k0 + sub * BK, m0, &ctrl->full[stage]);
+              if (B_KIN) tma_2d_g2s(sA + SLAB_DOUBLES, static_cast<const CUtensorMap*>(T.mapB), k0 + sub * BK, n0, &ctrl->full[stage]);
             }
           }
           __syncwarp();
@@ -377,15 +374,18 @@ struct TmapKeyHash {
 };
 
 struct TmapCache {
-  static constexpr int kChunk = 4096;  // maps per device chunk (chunks are never reallocated)
+  static constexpr int kChunk = 4096;          // maps per device chunk (chunks are never reallocated)
+  static constexpr size_t kMaxMaps = 1u << 20; // 128 MiB of descriptors: beyond that the cache is recycled
   std::mutex mu;
   std::unordered_map<TmapKey, const CUtensorMap*, TmapKeyHash> index;
   std::vector<CUtensorMap*> chunks;
-  int used_in_last = kChunk;
+  int cur_chunk = -1, used_in_cur = kChunk;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   cudaStream_t upload = nullptr;
   CUtensorMap* h_stage = nullptr;  // pinned
   int h_cap = 0;
+  struct Pending { CUtensorMap* dst; int chunk; };
+  std::vector<Pending> pending;    // created, not yet uploaded (h_stage[n] <-> pending[n])
 };
 
 int tmap_cache_get(tadev_ctx* ctx, TmapCache** out) {
@@ -406,6 +406,85 @@ int tmap_cache_get(tadev_ctx* ctx, TmapCache** out) {
   return TADEV_OK;
 }
 
+// encode the tiled map of one k-contiguous operand tile ([outer][k] doubles, box 16 x 128, SWIZZLE_128B) on the host
+int encode_map(TmapCache* c, CUtensorMap* hm, const double* ptr, int outer, int k) {
+  static const int promo_env = getenv("TADEV_TMAP_L2PROMO") ? atoi(getenv("TADEV_TMAP_L2PROMO")) : 3;
+  const CUtensorMapL2promotion l2promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)outer};
+  const cuuint64_t gstr[1] = {(cuuint64_t)k * 8};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = c->encode(hm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2promo,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    tadev_set_error("cuTensorMapEncodeTiled failed (%d) for tile %p [%d x %d]", (int)cr, (const void*)ptr, outer, k);
+    return TADEV_ECUDA;
+  }
+  return TADEV_OK;
+}
+
+// upload the maps created since the last flush on the cache's private stream and wait for them (c->mu held)
+int flush_pending_locked(TmapCache* c) {
+  auto& pending = c->pending;
+  if (pending.empty()) return TADEV_OK;
+  size_t i = 0;
+  while (i < pending.size()) {  // contiguous runs inside a chunk are uploaded with one copy each
+    size_t j = i + 1;
+    // (two chunks may be adjacent in the address space: one copy must not span two allocations)
+    while (j < pending.size() && pending[j].chunk == pending[j - 1].chunk && pending[j].dst == pending[j - 1].dst + 1) ++j;
+    TADEV_CHECK_CUDA(cudaMemcpyAsync(pending[i].dst, c->h_stage + i, sizeof(CUtensorMap) * (j - i), cudaMemcpyHostToDevice, c->upload));
+    i = j;
+  }
+  TADEV_CHECK_CUDA(cudaStreamSynchronize(c->upload));
+  pending.clear();
+  return TADEV_OK;
+}
+
+// cached device map of (ptr, outer, k); created (encoded, queued for upload) on a miss (c->mu held)
+int lookup_locked(TmapCache* c, const double* ptr, int outer, int k, const CUtensorMap** res, bool* created) {
+  TmapKey key{ptr, outer, k};
+  auto itf = c->index.find(key);
+  if (itf != c->index.end()) { *res = itf->second; return TADEV_OK; }
+  if (c->index.size() >= TmapCache::kMaxMaps) {
+    // bounded cache: long runs with changing tile addresses would otherwise grow it without limit. Nothing may
+    // still read a descriptor that is about to be overwritten, hence the device-wide sync (a rare event).
+    int rc = flush_pending_locked(c);
+    if (rc) return rc;
+    TADEV_CHECK_CUDA(cudaDeviceSynchronize());
+    c->index.clear();
+    c->cur_chunk = c->chunks.empty() ? -1 : 0;
+    c->used_in_cur = c->chunks.empty() ? TmapCache::kChunk : 0;
+  }
+  if (c->used_in_cur == TmapCache::kChunk) {
+    if (c->cur_chunk + 1 < (int)c->chunks.size()) ++c->cur_chunk;
+    else {
+      CUtensorMap* chunk = nullptr;
+      TADEV_CHECK_CUDA(cudaMalloc(&chunk, sizeof(CUtensorMap) * TmapCache::kChunk));
+      c->chunks.push_back(chunk);
+      c->cur_chunk = (int)c->chunks.size() - 1;
+    }
+    c->used_in_cur = 0;
+  }
+  CUtensorMap* dst = c->chunks[c->cur_chunk] + c->used_in_cur++;
+  if ((int)c->pending.size() == c->h_cap) {
+    const int ncap = c->h_cap ? c->h_cap * 2 : 1024;
+    CUtensorMap* nh = nullptr;
+    TADEV_CHECK_CUDA(cudaMallocHost(&nh, sizeof(CUtensorMap) * ncap));
+    if (c->h_stage) { memcpy(nh, c->h_stage, sizeof(CUtensorMap) * c->pending.size()); cudaFreeHost(c->h_stage); }
+    c->h_stage = nh; c->h_cap = ncap;
+  }
+  int rc = encode_map(c, c->h_stage + c->pending.size(), ptr, outer, k);
+  if (rc) { --c->used_in_cur; return rc; }
+  c->pending.push_back({dst, c->cur_chunk});
+  c->index.emplace(key, dst);
+  *res = dst;
+  if (created) *created = true;
+  return TADEV_OK;
+}
+
 // Resolve (and create on demand) the tensor maps of all k-contiguous operands of a batch.
 // New maps are encoded on the host and uploaded on a private stream which is synchronised
 // before returning, so any stream may use them afterwards.
@@ -416,47 +495,6 @@ int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* group
   int rc = tmap_cache_get(ctx, &c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
-  struct Pending { CUtensorMap* dst; int chunk; };
-  std::vector<Pending> pending;
-  static const int promo_env = getenv("TADEV_TMAP_L2PROMO") ? atoi(getenv("TADEV_TMAP_L2PROMO")) : 3;
-  const CUtensorMapL2promotion l2promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
-                                         : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                         : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  auto lookup = [&](const double* ptr, int outer, int k, const CUtensorMap** res) -> int {
-    TmapKey key{ptr, outer, k};
-    auto itf = c->index.find(key);
-    if (itf != c->index.end()) { *res = itf->second; return TADEV_OK; }
-    if (c->used_in_last == TmapCache::kChunk) {
-      CUtensorMap* chunk = nullptr;
-      TADEV_CHECK_CUDA(cudaMalloc(&chunk, sizeof(CUtensorMap) * TmapCache::kChunk));
-      c->chunks.push_back(chunk);
-      c->used_in_last = 0;
-    }
-    CUtensorMap* dst = c->chunks.back() + c->used_in_last++;
-    if ((int)pending.size() == c->h_cap) {
-      const int ncap = c->h_cap ? c->h_cap * 2 : 1024;
-      CUtensorMap* nh = nullptr;
-      TADEV_CHECK_CUDA(cudaMallocHost(&nh, sizeof(CUtensorMap) * ncap));
-      if (c->h_stage) { memcpy(nh, c->h_stage, sizeof(CUtensorMap) * pending.size()); cudaFreeHost(c->h_stage); }
-      c->h_stage = nh; c->h_cap = ncap;
-    }
-    CUtensorMap* hm = c->h_stage + pending.size();
-    const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)outer};
-    const cuuint64_t gstr[1] = {(cuuint64_t)k * 8};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = c->encode(hm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2promo,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-      tadev_set_error("cuTensorMapEncodeTiled failed (%d) for tile %p [%d x %d]", (int)cr, (const void*)ptr, outer, k);
-      return TADEV_ECUDA;
-    }
-    pending.push_back({dst, (int)c->chunks.size() - 1});
-    c->index.emplace(key, dst);
-    *res = dst;
-    return TADEV_OK;
-  };
   for (int gi = 0; gi < ngroups; ++gi) {
     const tadev_gemm_group& G = groups[gi];
     for (int ti = G.task_begin; ti < G.task_end; ++ti) {
@@ -464,36 +502,24 @@ int resolve_maps(tadev_ctx* ctx, int opA, int opB, const tadev_gemm_group* group
       WsTask& W = out[ti];
       W.A = T.A; W.B = T.B; W.k = T.k; W.pad = 0; W.mapA = nullptr; W.mapB = nullptr;
       if (T.k <= 0 || G.m <= 0 || G.n <= 0) continue;
-      if (a_kin) { rc = lookup(T.A, G.m, T.k, &W.mapA); if (rc) return rc; }
-      if (b_kin) { rc = lookup(T.B, G.n, T.k, &W.mapB); if (rc) return rc; }
+      const CUtensorMap* m = nullptr;
+      if (a_kin) { rc = lookup_locked(c, T.A, G.m, T.k, &m, nullptr); if (rc) return rc; W.mapA = m; }
+      if (b_kin) { rc = lookup_locked(c, T.B, G.n, T.k, &m, nullptr); if (rc) return rc; W.mapB = m; }
     }
   }
-  if (!pending.empty()) {
-    // contiguous runs inside a chunk are uploaded with one copy each
-    size_t i = 0;
-    while (i < pending.size()) {
-      size_t j = i + 1;
-      // (two chunks may be adjacent in the address space: one copy must not span two allocations)
-      while (j < pending.size() && pending[j].chunk == pending[j - 1].chunk && pending[j].dst == pending[j - 1].dst + 1) ++j;
-      TADEV_CHECK_CUDA(cudaMemcpyAsync(pending[i].dst, c->h_stage + i, sizeof(CUtensorMap) * (j - i),
-                                       cudaMemcpyHostToDevice, c->upload));
-      i = j;
-    }
-    TADEV_CHECK_CUDA(cudaStreamSynchronize(c->upload));
-  }
-  return TADEV_OK;
+  return flush_pending_locked(c);
 }
 
 template <int OPA, int OPB>
 int launch_ws_variant(cudaStream_t s, int grid, const tadev_gemm_group* d_groups, int ngroups, const WsTask* d_tasks,
-                      const int2* d_items, int total_tiles, int* d_counter, double alpha, int static_sched, int wave_sync) {
+                      const int2* d_items, const int* d_total, int* d_counter, double alpha, int static_sched, int wave_sync) {
   auto kern = gemm_grouped_f64_ws_kernel<OPA, OPB>;
   // the attribute is per device (context): set it on every launch (a cheap host-side call) rather than once per
   // process, so a process driving several devices gets the opt-in on each of them
   TADEV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   GemmTimingHook& hook = tadev_gemm_timing_hook();
   if (hook.before) TADEV_CHECK_CUDA(cudaEventRecord(hook.before, s));
-  kern<<<grid, NTHREADS, SMEM_BYTES, s>>>(d_groups, ngroups, d_tasks, d_items, total_tiles, d_counter, alpha, static_sched, wave_sync);
+  kern<<<grid, NTHREADS, SMEM_BYTES, s>>>(d_groups, ngroups, d_tasks, d_items, d_total, d_counter, alpha, static_sched, wave_sync);
   TADEV_CHECK_CUDA(cudaGetLastError());
   if (hook.after) TADEV_CHECK_CUDA(cudaEventRecord(hook.after, s));
   hook.before = hook.after = nullptr;
@@ -625,6 +651,7 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
     wave_sync = uniform ? 1 : 0;
   }
   memset((char*)h + off_c, 0, 16);
+  ((int32_t*)((char*)h + off_c))[2] = total_cta_tiles;  // [work counter, wave counter, number of work items, -]
   rc = tadev_stage_upload(ctx, s, d, h, off_c + 16, uploaded);
   if (rc) return rc;
   ctx->launches++;
@@ -633,11 +660,59 @@ int launch_gemm_grouped_f64_ws(tadev_ctx* ctx, cudaStream_t s, int opA, int opB,
   const int2* dp = (const int2*)((char*)d + off_p);
   int* dc = (int*)((char*)d + off_c);
   switch ((opA << 1) | opB) {
-    case 0: rc = launch_ws_variant<0, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched, wave_sync); break;
-    case 1: rc = launch_ws_variant<0, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched, wave_sync); break;
-    case 2: rc = launch_ws_variant<1, 0>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched, wave_sync); break;
-    case 3: rc = launch_ws_variant<1, 1>(s, grid, dg, ngroups, dt, dp, total_cta_tiles, dc, alpha, static_sched, wave_sync); break;
+    case 0: rc = launch_ws_variant<0, 0>(s, grid, dg, ngroups, dt, dp, dc + 2, dc, alpha, static_sched, wave_sync); break;
+    case 1: rc = launch_ws_variant<0, 1>(s, grid, dg, ngroups, dt, dp, dc + 2, dc, alpha, static_sched, wave_sync); break;
+    case 2: rc = launch_ws_variant<1, 0>(s, grid, dg, ngroups, dt, dp, dc + 2, dc, alpha, static_sched, wave_sync); break;
+    case 3: rc = launch_ws_variant<1, 1>(s, grid, dg, ngroups, dt, dp, dc + 2, dc, alpha, static_sched, wave_sync); break;
     default: tadev_set_error("launch_gemm_grouped_f64_ws: bad op flags %d %d", opA, opB); rc = TADEV_EINVAL;
   }
   return rc;  // ~StageLease records `done` after the launch and returns the slot
+}
+
+// Fast-path launch with DEVICE-resident lists (tilelist.cu): groups, tasks (with tensor maps), rasterised work items
+// and their count were produced by kernels on `s`; the host knows only upper bounds, so the full persistent grid is
+// launched and CTAs that find no work exit at once.
+int launch_gemm_ws_devlists(tadev_ctx* ctx, cudaStream_t s, int opA, int opB, double alpha, const tadev_gemm_group* d_groups,
+                            int ngroups, const void* d_wstasks, const int2* d_items, const int32_t* d_total, int32_t* d_sched,
+                            int wave_sync) {
+  int grid = ctx->num_sms - ctx->gemm_sm_reserve;
+  if (grid < 1) grid = 1;
+  static const int static_sched = getenv("TADEV_SCHED_STATIC") ? atoi(getenv("TADEV_SCHED_STATIC")) : 0;
+  ctx->launches++;
+  const WsTask* dt = static_cast<const WsTask*>(d_wstasks);
+  switch ((opA << 1) | opB) {
+    case 0: return launch_ws_variant<0, 0>(s, grid, d_groups, ngroups, dt, d_items, d_total, d_sched, alpha, static_sched, wave_sync);
+    case 1: return launch_ws_variant<0, 1>(s, grid, d_groups, ngroups, dt, d_items, d_total, d_sched, alpha, static_sched, wave_sync);
+    case 2: return launch_ws_variant<1, 0>(s, grid, d_groups, ngroups, dt, d_items, d_total, d_sched, alpha, static_sched, wave_sync);
+    case 3: return launch_ws_variant<1, 1>(s, grid, d_groups, ngroups, dt, d_items, d_total, d_sched, alpha, static_sched, wave_sync);
+  }
+  tadev_set_error("launch_gemm_ws_devlists: bad op flags %d %d", opA, opB);
+  return TADEV_EINVAL;
+}
+
+int tadev_ws_cached_map(tadev_ctx* ctx, const double* ptr, int outer, int k, const void** dev_map, bool* created) {
+  TmapCache* c = nullptr;
+  int rc = tmap_cache_get(ctx, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const CUtensorMap* m = nullptr;
+  rc = lookup_locked(c, ptr, outer, k, &m, created);
+  *dev_map = m;
+  return rc;
+}
+
+int tadev_ws_flush_new_maps(tadev_ctx* ctx) {
+  TmapCache* c = nullptr;
+  int rc = tmap_cache_get(ctx, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  return flush_pending_locked(c);
+}
+
+int tadev_ws_encode_map(tadev_ctx* ctx, void* h_dst128, const double* ptr, int outer, int k) {
+  TmapCache* c = nullptr;
+  int rc = tmap_cache_get(ctx, &c);
+  if (rc) return rc;
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  return encode_map(c, static_cast<CUtensorMap*>(h_dst128), ptr, outer, k);
 }

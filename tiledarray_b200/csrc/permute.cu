@@ -475,20 +475,57 @@ __global__ void scale_kernel(double* __restrict__ x, size_t n, double f) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) x[i] *= f;
 }
-__global__ void __launch_bounds__(256) sqnorm_kernel(const double* const* __restrict__ ptrs,
-                                                     const int64_t* __restrict__ sizes, double* __restrict__ out) {
-  const double* p = ptrs[blockIdx.x];
-  const int64_t n = sizes[blockIdx.x];
+// Squared Frobenius norms, two deterministic stages (bound: HBM): stage 1 reduces one chunk of kSqChunk doubles per
+// CTA (16-byte loads, 8 in flight per thread, fixed intra-chunk order), stage 2 adds a tile's chunk partials in
+// ascending order. The association depends only on the tile's own size, never on how many tiles share the launch,
+// so a tile's norm - and the float shape built from it - is reproducible bit for bit.
+constexpr int kSqChunk = 16384;
+__global__ void __launch_bounds__(256) sqnorm_partial_kernel(const double* const* __restrict__ ptrs, const int64_t* __restrict__ sizes,
+                                                             double* __restrict__ partial, int nchunks_max) {
+  const int tile = blockIdx.y;
+  const int64_t n = sizes[tile];
+  const int64_t lo = (int64_t)blockIdx.x * kSqChunk;
+  if (lo >= n) return;
+  const double* __restrict__ p = ptrs[tile] + lo;
+  const int len = (int)min((int64_t)kSqChunk, n - lo);
   double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += 256) { const double v = p[i]; acc += v * v; }
-  __shared__ double red[256];
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int sft = 128; sft > 0; sft >>= 1) {
-    if ((int)threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
-    __syncthreads();
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const double2* __restrict__ p2 = reinterpret_cast<const double2*>(p);
+    const int len2 = len >> 1;
+    int i = threadIdx.x;
+    for (; i + 7 * 256 < len2; i += 8 * 256) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p2[i + u * 256];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u].x * v[u].x + v[u].y * v[u].y;
+    }
+    for (; i < len2; i += 256) { const double2 v = p2[i]; acc += v.x * v.x + v.y * v.y; }
+    if ((len & 1) && threadIdx.x == 0) { const double v = p[len - 1]; acc += v * v; }
+  } else {
+    for (int i = threadIdx.x; i < len; i += 256) { const double v = p[i]; acc += v * v; }
   }
-  if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w];
+    partial[(size_t)tile * nchunks_max + blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) sqnorm_final_kernel(const int64_t* __restrict__ sizes, const double* __restrict__ partial,
+                                                           int nchunks_max, int ntiles, double* __restrict__ out) {
+  const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= ntiles) return;
+  const int64_t n = sizes[tile];
+  const int nch = (int)((n + kSqChunk - 1) / kSqChunk);
+  double t = 0.0;
+  for (int c = 0; c < nch; ++c) t += partial[(size_t)tile * nchunks_max + c];
+  out[tile] = t;
 }
 // splitmix64-based counter RNG: value depends only on (seed, global element offset)
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -532,14 +569,40 @@ extern "C" int tadev_scale_f64(tadev_ctx* ctx, tadev_stream s, size_t n, double*
   return TADEV_OK;
 }
 extern "C" int tadev_tile_sqnorms_f64(tadev_ctx* ctx, tadev_stream s, int ntiles, const double* const* d_ptrs,
-                                      const int64_t* d_sizes, double* d_out) {
+                                      const int64_t* d_sizes, int64_t max_elems, double* d_out) {
   TADEV_REQUIRE(ctx, "tadev_tile_sqnorms_f64: null ctx");
   if (ntiles <= 0) return TADEV_OK;
-  TADEV_REQUIRE(d_ptrs && d_sizes && d_out, "tadev_tile_sqnorms_f64: null arrays");
-  sqnorm_kernel<<<ntiles, 256, 0, (cudaStream_t)s>>>(d_ptrs, d_sizes, d_out);
-  ctx->launches++;
-  TADEV_CHECK_CUDA(cudaGetLastError());
+  TADEV_REQUIRE(d_ptrs && d_sizes && d_out && max_elems >= 0, "tadev_tile_sqnorms_f64: bad arguments");
+  TADEV_REQUIRE(ntiles <= 65535, "tadev_tile_sqnorms_f64: at most 65535 tiles per call");
+  const int64_t nch = std::max<int64_t>(1, (max_elems + kSqChunk - 1) / kSqChunk);
+  TADEV_REQUIRE(nch < (1ll << 31), "tadev_tile_sqnorms_f64: tile too large");
+  double* partial = nullptr;
+  int rc = tadev_alloc(ctx, (size_t)ntiles * (size_t)nch * 8, (void**)&partial, s);
+  if (rc) return rc;
+  sqnorm_partial_kernel<<<dim3((unsigned)nch, (unsigned)ntiles), 256, 0, (cudaStream_t)s>>>(d_ptrs, d_sizes, partial, (int)nch);
+  sqnorm_final_kernel<<<(ntiles + 255) / 256, 256, 0, (cudaStream_t)s>>>(d_sizes, partial, (int)nch, ntiles, d_out);
+  ctx->launches += 2;
+  cudaError_t e = cudaGetLastError();
+  tadev_free(ctx, partial, s);
+  TADEV_CHECK_CUDA(e);
   return TADEV_OK;
+}
+// one tile, scalar handed to the host (Tensor::squared_norm): stages (ptr, size) on the device, reduces, copies back
+extern "C" int tadev_sqnorm_f64(tadev_ctx* ctx, tadev_stream s, size_t n, const double* d_x, double* h_out) {
+  TADEV_REQUIRE(ctx && h_out, "tadev_sqnorm_f64: null");
+  *h_out = 0.0;
+  if (!n) return TADEV_OK;
+  TADEV_REQUIRE(d_x, "tadev_sqnorm_f64: null tile");
+  struct { const double* p; int64_t n; double out; } h{d_x, (int64_t)n, 0.0};
+  char* d = nullptr;
+  int rc = tadev_alloc(ctx, sizeof(h), (void**)&d, s);
+  if (rc) return rc;
+  rc = tadev_memcpy_h2d(ctx, d, &h, 16, s);  // pageable source: staged before the call returns
+  if (!rc) rc = tadev_tile_sqnorms_f64(ctx, s, 1, (const double* const*)d, (const int64_t*)(d + 8), (int64_t)n, (double*)(d + 16));
+  if (!rc) rc = tadev_memcpy_d2h(ctx, h_out, d + 16, 8, s);
+  if (!rc) rc = tadev_stream_sync(ctx, s);
+  tadev_free(ctx, d, s);
+  return rc;
 }
 extern "C" int tadev_fill_uniform_f64(tadev_ctx* ctx, tadev_stream s, double* d_x, size_t n, uint64_t seed,
                                       uint64_t offset) {

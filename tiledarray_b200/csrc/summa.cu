@@ -17,12 +17,14 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <numeric>
 #include <string>
 
 #include "common.h"
 #include "summa_schedule.h"
+#include "tilelist.h"
 
 #define TADEV_CHECK_NCCL(expr)                                                                   \
   do {                                                                                           \
@@ -315,12 +317,6 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
   brange.assign(nb, {0, 0});
   max_bytes = 0; b_cache_elems = 0;
   b_cache_off.assign(S.steps.size(), 0);
-  for (size_t si = 0; si < S.steps.size(); ++si) {
-    size_t e = 0;
-    for (int j : S.steps[si].b_cols) e += pad2(tile_b_elems(S.steps[si].k, j));
-    b_cache_off[si] = b_cache_elems;
-    if (b_cache && (S.steps[si].bcast_b || b_stg)) b_cache_elems += e;
-  }
   // ---- global windows. NCCL may reorder the operations inside one group, so two ranks of a
   // communicator must put the same broadcasts into the same group: window boundaries are therefore
   // derived from replicated data only (globally active steps, a byte bound that is the maximum
@@ -343,10 +339,29 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
       size_t need = 0;
       if (a_stg || Pc > 1) need += *std::max_element(per_r.begin(), per_r.end());
       if ((b_stg || Pr > 1) && !b_cache) need += *std::max_element(per_c.begin(), per_c.end());
-      const int wcap = (nwin == 0) ? 1 : W;  // the very first window is a single step: the pipeline fills quickly
+      // windows ramp up geometrically (1, 2, 4, ... W steps): the panels of window n+1 travel while window n computes,
+      // so only the first, single-step window is exposed; a full-size second window had its whole broadcast in the
+      // open (block-sparse config 3 on 4 GPUs: 11 of 55 ms, profiles/r02_trace_C3_n4_before_ramp.log)
+      const int wcap = nwin < 30 ? std::min(W, 1 << nwin) : W;
       if (cnt > 0 && (cnt >= wcap || gbytes + need > kMaxWindowBytes)) { ++nwin; cnt = 0; gbytes = 0; win_of_k[k] = nwin; }
       ++cnt; gbytes += need;
     }
+  }
+  // B cache layout: the panels one root row sends in one window are contiguous (they travel as ONE broadcast):
+  // order (global window, root row k % Pr, step)
+  if (b_cache) {
+    int nwin_total = 0;
+    for (int k = 0; k < Kt; ++k) nwin_total = std::max(nwin_total, win_of_k[k] + 1);
+    std::vector<std::vector<size_t>> by_slot((size_t)std::max(nwin_total, 1) * Pr);
+    for (size_t si = 0; si < S.steps.size(); ++si)
+      if (S.steps[si].bcast_b || b_stg) by_slot[(size_t)win_of_k[S.steps[si].k] * Pr + S.steps[si].k % Pr].push_back(si);
+    for (auto& v : by_slot)
+      for (size_t si : v) {
+        size_t e = 0;
+        for (int j : S.steps[si].b_cols) e += pad2(tile_b_elems(S.steps[si].k, j));
+        b_cache_off[si] = b_cache_elems;
+        b_cache_elems += e;
+      }
   }
   for (int b = 0; b < nb; ++b) {
     const int L = (int)my_rows.size();
@@ -430,14 +445,25 @@ extern "C" int tadev_summa_comm_trace(int Pr, int Pc, int r, int c, const tadev_
     if (n < capacity && comm && group && k && root && bytes) { comm[n] = cm; group[n] = g; k[n] = kk; root[n] = rt; bytes[n] = (int64_t)by; }
     ++n;
   };
+  // one broadcast per (window, communicator, root): the root's panels of all steps of the window travel together
   for (int b = 0; b < X.nb; ++b)
     for (const Window& win : X.bwins[b]) {
-      bool any = false;
-      for (int x : win.steps) { const BlockStep& bs = X.bsteps[b][x]; if (bs.bcast_a) { emit(0, bs.st->k, bs.st->k % Pc, bs.a_elems * 8); any = true; } }
-      if (any) ++g;
-      any = false;
-      for (int x : win.steps) { const BlockStep& bs = X.bsteps[b][x]; if (bs.bcast_b) { emit(1, bs.st->k, bs.st->k % Pr, bs.b_elems * 8); any = true; } }
-      if (any) ++g;
+      for (int which = 0; which < 2; ++which) {
+        const int nroots = which == 0 ? Pc : Pr;
+        bool any = false;
+        for (int root = 0; root < nroots; ++root) {
+          size_t by = 0;
+          int first_k = -1;
+          for (int x : win.steps) {
+            const BlockStep& bs = X.bsteps[b][x];
+            if (!(which == 0 ? bs.bcast_a : bs.bcast_b) || bs.st->k % nroots != root) continue;
+            by += (which == 0 ? bs.a_elems : bs.b_elems) * 8;
+            if (first_k < 0) first_k = bs.st->k;
+          }
+          if (by) { emit(which, first_k, root, by); any = true; }
+        }
+        if (any) ++g;
+      }
     }
   *n_out = n;
   TADEV_REQUIRE(n <= capacity || !comm, "tadev_summa_comm_trace: capacity %lld < %lld", (long long)capacity, (long long)n);
@@ -476,6 +502,8 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   cudaStream_t sc = ctx->comm_stream[0];                   // NCCL panel broadcasts
   cudaStream_t sh = ctx->comm_stream[1];                   // host -> device panel staging
 
+  const auto host_t0 = std::chrono::steady_clock::now();
+  auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
   SummaWindows X;
   build_summa_windows(Pr, Pc, r, c, P, X);
   SummaSchedule& S = X.S;
@@ -598,6 +626,8 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
       return local_rc ? local_rc : arc;
     }
   } else if (local_rc) return local_rc;
+  static const bool trace_host = getenv("TADEV_SUMMA_TRACE") && atoi(getenv("TADEV_SUMMA_TRACE"));
+  if (trace_host) fprintf(stderr, "[tadev summa rank %d] host: schedule+windows+resources ready at %.3f ms\n", ctx->rank, host_ms());
   TADEV_CHECK_CUDA(cudaEventRecord(ev_start, s0));
   TADEV_CHECK_CUDA(cudaStreamWaitEvent(sc, ev_start, 0));
   TADEV_CHECK_CUDA(cudaStreamWaitEvent(sh, ev_start, 0));
@@ -636,66 +666,36 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   int64_t wcount = 0;                                     // global window counter -> ring slot
   std::vector<char> b_cached(S.steps.size(), 0);
 
-  // Stage one panel: returns device pointers of its tiles. `mine` = I own the source tiles.
-  // host-resident sources are uploaded (sh), device-resident ones are used in place when they need
-  // no transport, broadcast in place when contiguous, or packed (sc).
   std::vector<uint64_t> prov_tok;
   std::vector<double*> prov_dst;
-  auto stage_panel = [&](bool on_host, tadev_tile_provider provider, void* user, bool needs_bcast, bool mine,
-                         const std::vector<const double*>& src, const std::vector<size_t>& elems, double* dest,
-                         bool* used_dest, bool* did_h2d, std::vector<const double*>& out) -> int {
-    out.assign(src.size(), nullptr);
-    *used_dest = false;
-    if (!needs_bcast && !on_host && !provider) { for (size_t n = 0; n < src.size(); ++n) out[n] = src[n]; return TADEV_OK; }
-    double* panel = dest;
-    bool inplace = false;
-    if (mine) {
-      if (provider) {  // lazy tiles: src[] holds opaque tokens; the provider fills the panel on the staging stream
-        prov_tok.clear(); prov_dst.clear();
-        size_t o = 0;
-        for (size_t n = 0; n < src.size(); ++n) {
-          prov_tok.push_back((uint64_t)reinterpret_cast<uintptr_t>(src[n]));
-          prov_dst.push_back(panel + o);
-          o += pad2(elems[n]);
-        }
-        if (!src.empty()) {
-          int rc = provider(user, (tadev_stream)sh, (int)src.size(), prov_tok.data(), prov_dst.data(), elems.data());
-          if (rc) return rc;
-          lazy_tiles += (int64_t)src.size();
-        }
-        *did_h2d = true;
-      } else if (on_host) {
-        size_t o = 0;
-        for (size_t n = 0; n < src.size(); ++n) {
-          TADEV_CHECK_CUDA(cudaMemcpyAsync(panel + o, src[n], elems[n] * 8, cudaMemcpyHostToDevice, sh));
-          h2d_bytes += (int64_t)elems[n] * 8;
-          o += pad2(elems[n]);
-        }
-        *did_h2d = true;
-      } else {
-        inplace = true;
-        size_t off = 0;
-        for (size_t n = 0; n < src.size(); ++n) {
-          if (src[n] != src[0] + off || (reinterpret_cast<uintptr_t>(src[n]) & 15)) inplace = false;
-          off += pad2(elems[n]);
-        }
-        if (inplace) panel = const_cast<double*>(src[0]);
-        else {
-          size_t o = 0;
-          for (size_t n = 0; n < src.size(); ++n) {
-            TADEV_CHECK_CUDA(cudaMemcpyAsync(panel + o, src[n], elems[n] * 8, cudaMemcpyDeviceToDevice, sc));
-            o += pad2(elems[n]);
-          }
-        }
-      }
-    }
-    *used_dest = !inplace;
-    size_t o = 0;
-    for (size_t n = 0; n < src.size(); ++n) { out[n] = panel + o; o += pad2(elems[n]); }
-    return TADEV_OK;
-  };
 
+  // ---- tile lists are built on the device (tilelist.cu): the host stages O(rows + cols) panel-tile tables per
+  //      step, the O(pairs) enumeration / chaining / rasterisation runs as kernels on the compute stream.
+  //      TADEV_HOST_LISTS=1 selects the host-built lists (A/B comparison; the two paths give identical launches).
+  const bool host_lists = getenv("TADEV_HOST_LISTS") && atoi(getenv("TADEV_HOST_LISTS"));
+  const bool use_tl = !host_lists;
+  TileListBuilder TL;
+  const int ncl = c < Nt ? (Nt - c + Pc - 1) / Pc : 0;
+  float list_ms = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> list_events;
+  if (use_tl) {
+    size_t max_tasks = 1;
+    for (int b = 0; b < nb; ++b)
+      for (const Window& win : bwins[b]) {
+        size_t t = 0;
+        for (int x : win.steps) { const BlockStep& bs = bsteps[b][x]; if (bs.compute) t += bs.a_rows.size() * bs.st->b_cols.size(); }
+        max_tasks = std::max(max_tasks, t);
+      }
+    int rc = TL.init(ctx, s0, Pr, Pc, r, c, Mt, Nt, Kt, P.m_ext, P.n_ext, P.k_ext, P.a_norms, P.b_norms, P.c_norms, P.threshold,
+                     P.accumulate, max_tasks);
+    if (TL.d_base) R.buffers.push_back(TL.d_base);
+    if (rc) return rc;
+  }
+  const bool a_kin = P.opA == TADEV_OP_N, b_kin = P.opB == TADEV_OP_T;  // operand stored k-contiguous: needs a tensor map
+
+  if (trace_host) fprintf(stderr, "[tadev summa rank %d] host: list builder ready at %.3f ms\n", ctx->rank, host_ms());
   for (int b = 0; b < nb; ++b) {
+    bool block_listed = false;  // the block's result-tile table is on the device (first listed window)
     // ---- device addresses of this block's result tiles
     const int cslot = b & 1;
     if (c_host) {
@@ -725,73 +725,148 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
       size_t cursor = 0;
       bool any_bcast = false, any_h2d = false, ring_touched = false;
       std::vector<std::vector<const double*>> a_ptrs(win.steps.size()), b_ptrs(win.steps.size());
+      std::vector<char> a_trans(win.steps.size(), 0), b_trans(win.steps.size(), 0);  // panel lives in the ring / B cache
       std::vector<Bcast> row_bcasts, col_bcasts;
       if (need_ring && win.bytes > 0 && buf_used[d]) {  // the GEMM that last read this slot is done
         TADEV_CHECK_CUDA(cudaStreamWaitEvent(sc, buf_free[d], 0));
         TADEV_CHECK_CUDA(cudaStreamWaitEvent(sh, buf_free[d], 0));
       }
+      // ---- panels of this window. Panels that travel are merged per (communicator, root): the root's panels of
+      //      all steps of the window form ONE contiguous byte range (in its arena when the array was laid out panel by
+      //      panel, else packed into the ring) and go out as ONE ncclBroadcast. Block-sparse panels are small (config 3:
+      //      ~26 MB per step); one NCCL operation per step ran at ~25 GB/s (one channel each), one per root and window
+      //      uses all channels (profiles/r02_c3_n2_*.json).
+      struct Panel {
+        size_t wsi, si; bool is_a, bcast, mine, to_cache; int root; size_t elems;
+        std::vector<const double*> src; std::vector<size_t> el;
+      };
+      std::vector<Panel> panels;
       for (size_t wsi = 0; wsi < win.steps.size(); ++wsi) {
         const BlockStep& bs = bsteps[b][win.steps[wsi]];
         const SummaStep& st = *bs.st;
         const int k = st.k;
         const size_t si = (size_t)(bs.st - &S.steps[0]);
-        std::vector<const double*> src;
-        std::vector<size_t> el;
-        // ---- A panel (travels along my grid row; root column k % Pc)
-        if (bs.bcast_a || bs.compute) {
-          const bool mine = (c == k % Pc);
-          src.clear(); el.clear();
+        if (bs.bcast_a || bs.compute) {  // A panel (travels along my grid row; root column k % Pc)
+          Panel p{wsi, si, true, bs.bcast_a, c == k % Pc, false, k % Pc, bs.a_elems, {}, {}};
           for (int i : bs.a_rows) {
             const double* tp = P.a_tiles[(size_t)i * Kt + k];
-            TADEV_REQUIRE(!mine || tp, "tadev_summa_f64: A tile (%d,%d) is owned by this rank but has no data", i, k);
-            src.push_back(tp); el.push_back(tile_a_elems(i, k));
+            TADEV_REQUIRE(!p.mine || tp, "tadev_summa_f64: A tile (%d,%d) is owned by this rank but has no data", i, k);
+            p.src.push_back(tp); p.el.push_back(tile_a_elems(i, k));
           }
-          bool used = false;
-          int rc = stage_panel(a_host, a_lazy ? P.a_provider : nullptr, P.a_user, bs.bcast_a, mine, src, el,
-                               buf ? buf + cursor : nullptr, &used, &any_h2d, a_ptrs[wsi]);
-          if (rc) return rc;
-          if (used) { cursor += bs.a_elems; ring_touched = true; }
-          if (bs.bcast_a) {
-            row_bcasts.push_back({const_cast<double*>(a_ptrs[wsi][0]), bs.a_elems * 8, k % Pc});
-            bcast_bytes += (int64_t)bs.a_elems * 8;
-            any_bcast = true;
-          }
+          panels.push_back(std::move(p));
         }
-        // ---- B panel (travels along my grid column; root row k % Pr); cached across row blocks
-        if (bs.bcast_b || bs.compute) {
+        if (bs.bcast_b || bs.compute) {  // B panel (travels along my grid column; root row k % Pr); cached across row blocks
           const bool to_cache = b_cache && (st.bcast_b || b_stg);
           if (to_cache && b_cached[si]) {
             size_t o = 0;
-            b_ptrs[wsi].clear();
             for (int j : st.b_cols) { b_ptrs[wsi].push_back(bcache + b_cache_off[si] + o); o += pad2(tile_b_elems(k, j)); }
-          } else {
-            const bool mine = (r == k % Pr);
-            src.clear(); el.clear();
-            for (int j : st.b_cols) {
-              const double* tp = P.b_tiles[(size_t)k * Nt + j];
-              TADEV_REQUIRE(!mine || tp, "tadev_summa_f64: B tile (%d,%d) is owned by this rank but has no data", k, j);
-              src.push_back(tp); el.push_back(tile_b_elems(k, j));
-            }
-            double* dest = to_cache ? bcache + b_cache_off[si] : (buf ? buf + cursor : nullptr);
-            bool used = false;
-            int rc = stage_panel(b_host, b_lazy ? P.b_provider : nullptr, P.b_user, bs.bcast_b, mine, src, el, dest, &used,
-                                 &any_h2d, b_ptrs[wsi]);
-            if (rc) return rc;
-            if (used && !to_cache) { cursor += bs.b_elems; ring_touched = true; }
-            if (to_cache) {
-              // an in-place broadcast source lives outside the cache: mirror it so later blocks find it
-              if (!used && !st.b_cols.empty()) {
-                TADEV_CHECK_CUDA(cudaMemcpyAsync(dest, b_ptrs[wsi][0], bs.b_elems * 8, cudaMemcpyDeviceToDevice, sc));
-              }
-              b_cached[si] = 1;
-            }
-            if (bs.bcast_b) {
-              col_bcasts.push_back({const_cast<double*>(b_ptrs[wsi][0]), bs.b_elems * 8, k % Pr});
-              bcast_bytes += (int64_t)bs.b_elems * 8;
-              any_bcast = true;
-            }
+            b_trans[wsi] = 1;
+            continue;
           }
+          Panel p{wsi, si, false, bs.bcast_b, r == k % Pr, to_cache, k % Pr, bs.b_elems, {}, {}};
+          for (int j : st.b_cols) {
+            const double* tp = P.b_tiles[(size_t)k * Nt + j];
+            TADEV_REQUIRE(!p.mine || tp, "tadev_summa_f64: B tile (%d,%d) is owned by this rank but has no data", k, j);
+            p.src.push_back(tp); p.el.push_back(tile_b_elems(k, j));
+          }
+          panels.push_back(std::move(p));
         }
+      }
+      // travelling panels first, grouped by (operand, root), steps ascending inside a group
+      std::stable_sort(panels.begin(), panels.end(), [](const Panel& x, const Panel& y) {
+        const int kx = (x.is_a ? 0 : 2) + (x.bcast ? 0 : 1), ky = (y.is_a ? 0 : 2) + (y.bcast ? 0 : 1);
+        if (kx != ky) return kx < ky;
+        if (x.bcast && x.root != y.root) return x.root < y.root;
+        return x.wsi < y.wsi;
+      });
+      for (size_t p0 = 0; p0 < panels.size();) {
+        size_t p1 = p0 + 1;
+        if (panels[p0].bcast)
+          while (p1 < panels.size() && panels[p1].bcast && panels[p1].is_a == panels[p0].is_a && panels[p1].root == panels[p0].root) ++p1;
+        const Panel& first = panels[p0];
+        const bool on_host = first.is_a ? a_host : b_host;
+        const tadev_tile_provider provider = first.is_a ? (a_lazy ? P.a_provider : nullptr) : (b_lazy ? P.b_provider : nullptr);
+        void* user = first.is_a ? P.a_user : P.b_user;
+        auto& ptrs_of = first.is_a ? a_ptrs : b_ptrs;
+        auto& trans_of = first.is_a ? a_trans : b_trans;
+        size_t total = 0;
+        for (size_t q = p0; q < p1; ++q) total += panels[q].elems;
+        // in place: device-resident source tiles that need no transport, or a root whose tiles are one contiguous range
+        bool inplace = !on_host && !provider && (!first.bcast || first.mine);
+        if (inplace && first.bcast) {
+          const double* base = nullptr;
+          size_t off = 0;
+          for (size_t q = p0; q < p1 && inplace; ++q)
+            for (size_t n = 0; n < panels[q].src.size(); ++n) {
+              if (!base) base = panels[q].src[n];
+              if (panels[q].src[n] != base + off || (reinterpret_cast<uintptr_t>(panels[q].src[n]) & 15)) { inplace = false; break; }
+              off += pad2(panels[q].el[n]);
+            }
+        }
+        double* dest = nullptr;
+        if (!inplace || first.to_cache) dest = first.to_cache ? bcache + b_cache_off[first.si] : (buf ? buf + cursor : nullptr);
+        size_t doff = 0;
+        const double* first_ptr = nullptr;
+        for (size_t q = p0; q < p1; ++q) {
+          const Panel& pn = panels[q];
+          auto& out = ptrs_of[pn.wsi];
+          out.assign(pn.src.size(), nullptr);
+          if (inplace) {
+            for (size_t n = 0; n < pn.src.size(); ++n) out[n] = pn.src[n];
+          } else {
+            TADEV_REQUIRE(dest || pn.src.empty(), "tadev_summa_f64: internal: no staging buffer for a panel");
+            double* panel = dest + doff;
+            if (pn.mine || !pn.bcast) {  // I hold the source: materialise the panel
+              if (provider) {  // lazy tiles: src[] holds opaque tokens; the provider fills the panel on the staging stream
+                prov_tok.clear(); prov_dst.clear();
+                size_t o = 0;
+                for (size_t n = 0; n < pn.src.size(); ++n) {
+                  prov_tok.push_back((uint64_t)reinterpret_cast<uintptr_t>(pn.src[n]));
+                  prov_dst.push_back(panel + o);
+                  o += pad2(pn.el[n]);
+                }
+                if (!pn.src.empty()) {
+                  int rc = provider(user, (tadev_stream)sh, (int)pn.src.size(), prov_tok.data(), prov_dst.data(), pn.el.data());
+                  if (rc) return rc;
+                  lazy_tiles += (int64_t)pn.src.size();
+                }
+                any_h2d = true;
+              } else if (on_host) {
+                size_t o = 0;
+                for (size_t n = 0; n < pn.src.size(); ++n) {
+                  TADEV_CHECK_CUDA(cudaMemcpyAsync(panel + o, pn.src[n], pn.el[n] * 8, cudaMemcpyHostToDevice, sh));
+                  h2d_bytes += (int64_t)pn.el[n] * 8;
+                  o += pad2(pn.el[n]);
+                }
+                any_h2d = true;
+              } else {  // device-resident but scattered: pack
+                size_t o = 0;
+                for (size_t n = 0; n < pn.src.size(); ++n) {
+                  TADEV_CHECK_CUDA(cudaMemcpyAsync(panel + o, pn.src[n], pn.el[n] * 8, cudaMemcpyDeviceToDevice, sc));
+                  o += pad2(pn.el[n]);
+                }
+              }
+            }
+            size_t o = 0;
+            for (size_t n = 0; n < pn.src.size(); ++n) { out[n] = panel + o; o += pad2(pn.el[n]); }
+            trans_of[pn.wsi] = 1;
+          }
+          if (!first_ptr && !out.empty()) first_ptr = out[0];
+          doff += pn.elems;
+          if (pn.to_cache) b_cached[pn.si] = 1;
+        }
+        if (!inplace && !first.to_cache) { cursor += total; ring_touched = true; }
+        if (inplace && first.to_cache && total && first_ptr) {
+          // an in-place broadcast source lives outside the cache: mirror it so later blocks find it
+          TADEV_CHECK_CUDA(cudaMemcpyAsync(dest, first_ptr, total * 8, cudaMemcpyDeviceToDevice, sc));
+          ring_touched = true;  // (a copy on sc the GEMM must wait for)
+        }
+        if (first.bcast && total) {
+          (first.is_a ? row_bcasts : col_bcasts).push_back({const_cast<double*>(first_ptr), total * 8, first.root});
+          bcast_bytes += (int64_t)total * 8;
+          any_bcast = true;
+        }
+        p0 = p1;
       }
       // ---- ordering: H2D (sh) -> broadcasts (sc) -> GEMM (s0)
       if (any_h2d) {
@@ -824,8 +899,101 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
         TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, panel_ready[d], 0));
       }
 
-      // ---- grouped GEMM descriptors of this window: chain contributions per result tile
+      // ---- tile lists of this window, built on the device from staged panel-tile tables
+      if (use_tl) {
+        const int li0 = brange[b].first, li1 = brange[b].second, nrows = li1 - li0;
+        std::vector<int> wsteps;
+        for (size_t wsi = 0; wsi < win.steps.size(); ++wsi) if (bsteps[b][win.steps[wsi]].compute) wsteps.push_back((int)wsi);
+        if (!wsteps.empty() && nrows > 0 && ncl > 0) {
+          const int nws = (int)wsteps.size();
+          // fast (TMA) kernel needs 16-byte aligned operand rows: even leading dimensions, aligned tile addresses
+          bool fast = !ctx->force_generic_gemm;
+          size_t nmaps = 0;
+          for (int wsi : wsteps) {
+            const BlockStep& bs = bsteps[b][win.steps[wsi]];
+            const int64_t kx = P.k_ext[bs.st->k];
+            for (size_t ai = 0; ai < bs.a_rows.size() && fast; ++ai)
+              fast = !(((a_kin ? kx : P.m_ext[bs.a_rows[ai]]) & 1) || (reinterpret_cast<uintptr_t>(a_ptrs[wsi][ai]) & 15));
+            for (size_t bj = 0; bj < bs.st->b_cols.size() && fast; ++bj)
+              fast = !(((b_kin ? kx : P.n_ext[bs.st->b_cols[bj]]) & 1) || (reinterpret_cast<uintptr_t>(b_ptrs[wsi][bj]) & 15));
+            if (a_kin && a_trans[wsi]) nmaps += bs.a_rows.size();
+            if (b_kin && b_trans[wsi]) nmaps += bs.st->b_cols.size();
+          }
+          auto al = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
+          const size_t o_k = 0, o_a = al((size_t)nws * 4, 16), o_b = o_a + (size_t)nws * nrows * sizeof(TlTile);
+          const size_t o_c = o_b + (size_t)nws * ncl * sizeof(TlTile);
+          const size_t o_m = al(o_c + (block_listed ? 0 : (size_t)nrows * ncl * 8), 128), total_b = o_m + (fast ? nmaps : 0) * 128;
+          StageLease L;
+          int rc = L.acquire(ctx, s0, total_b + 128);
+          if (rc) return rc;
+          // (the staging buffers come from cudaMalloc / cudaMallocHost: 256-byte aligned, as tensor maps require)
+          char* h = static_cast<char*>(L.h);
+          char* dblk = static_cast<char*>(L.d);
+          int32_t* hk = reinterpret_cast<int32_t*>(h + o_k);
+          TlTile* ha = reinterpret_cast<TlTile*>(h + o_a);
+          TlTile* hb = reinterpret_cast<TlTile*>(h + o_b);
+          memset(ha, 0, (size_t)nws * nrows * sizeof(TlTile));
+          memset(hb, 0, (size_t)nws * ncl * sizeof(TlTile));
+          size_t nm = 0;
+          bool created = false;
+          for (int x = 0; x < nws; ++x) {
+            const int wsi = wsteps[x];
+            const BlockStep& bs = bsteps[b][win.steps[wsi]];
+            const int k = bs.st->k;
+            const int kx = (int)P.k_ext[k];
+            hk[x] = k;
+            for (size_t ai = 0; ai < bs.a_rows.size(); ++ai) {
+              const int i = bs.a_rows[ai];
+              TlTile& t = ha[(size_t)x * nrows + ((i - r) / Pr - li0)];
+              t.ptr = a_ptrs[wsi][ai];
+              if (fast && a_kin && kx > 0) {
+                if (a_trans[wsi]) {
+                  rc = tadev_ws_encode_map(ctx, h + o_m + nm * 128, t.ptr, (int)P.m_ext[i], kx);
+                  t.map = dblk + o_m + nm * 128; ++nm;
+                } else rc = tadev_ws_cached_map(ctx, t.ptr, (int)P.m_ext[i], kx, &t.map, &created);
+                if (rc) return rc;
+              }
+            }
+            for (size_t bj = 0; bj < bs.st->b_cols.size(); ++bj) {
+              const int j = bs.st->b_cols[bj];
+              TlTile& t = hb[(size_t)x * ncl + (j - c) / Pc];
+              t.ptr = b_ptrs[wsi][bj];
+              if (fast && b_kin && kx > 0) {
+                if (b_trans[wsi]) {
+                  rc = tadev_ws_encode_map(ctx, h + o_m + nm * 128, t.ptr, (int)P.n_ext[j], kx);
+                  t.map = dblk + o_m + nm * 128; ++nm;
+                } else rc = tadev_ws_cached_map(ctx, t.ptr, (int)P.n_ext[j], kx, &t.map, &created);
+                if (rc) return rc;
+              }
+            }
+          }
+          double* const* d_cstaged = nullptr;
+          if (!block_listed) {
+            double** hc = reinterpret_cast<double**>(h + o_c);
+            for (int lr = 0; lr < nrows; ++lr)
+              for (int lj = 0; lj < ncl; ++lj) hc[(size_t)lr * ncl + lj] = c_dev[(size_t)my_rows[li0 + lr] * Nt + (c + lj * Pc)];
+            d_cstaged = reinterpret_cast<double* const*>(dblk + o_c);
+          }
+          if (created && (rc = tadev_ws_flush_new_maps(ctx))) return rc;
+          rc = tadev_stage_upload(ctx, s0, L.d, L.h, total_b, L.uploaded);
+          if (rc) return rc;
+          cudaEvent_t l0 = nullptr, l1 = nullptr, g0 = nullptr, g1 = nullptr;
+          if (R.event(&l0, cudaEventDefault) == TADEV_OK && R.event(&l1, cudaEventDefault) == TADEV_OK) list_events.push_back({l0, l1});
+          if (R.event(&g0, cudaEventDefault) == TADEV_OK && R.event(&g1, cudaEventDefault) == TADEV_OK) gemm_events.push_back({g0, g1});
+          mark("tables_up", b, wi, s0);
+          rc = TL.build_and_launch(P.opA, P.opB, P.alpha, li0, li1, nws, reinterpret_cast<const int32_t*>(dblk + o_k),
+                                   reinterpret_cast<const TlTile*>(dblk + o_a), reinterpret_cast<const TlTile*>(dblk + o_b), d_cstaged,
+                                   fast, l0, l1, g0, g1);
+          if (rc) return rc;
+          block_listed = true;
+          ++nlaunches;
+          if (trace_host) fprintf(stderr, "[tadev summa rank %d] host: block %d window %d lists+gemm enqueued at %.3f ms\n", ctx->rank, b, wi, host_ms());
+          mark("gemm_done", b, wi, s0);
+        }
+      }
+      // ---- (TADEV_HOST_LISTS=1) grouped GEMM descriptors of this window built on the host: chain contributions per result tile
       contrib.clear();
+      if (!use_tl)
       for (size_t wsi = 0; wsi < win.steps.size(); ++wsi) {
         const BlockStep& bs = bsteps[b][win.steps[wsi]];
         if (!bs.compute) continue;
@@ -879,6 +1047,10 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     }
 
     // ---- block epilogue: zero-fill untouched non-zero tiles, then hand the block to the host
+    if (use_tl && block_listed) {
+      int rc = TL.zero_untouched(brange[b].first, brange[b].second);
+      if (rc) return rc;
+    } else
     for (int x = brange[b].first; x < brange[b].second; ++x)
       for (int j = c; j < Nt; j += Pc) {
         const size_t key = (size_t)my_rows[x] * Nt + j;
@@ -912,6 +1084,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     TADEV_CHECK_CUDA(cudaStreamWaitEvent(s0, ev_aux, 0));
   }
   TADEV_CHECK_CUDA(cudaEventRecord(ev_end, s0));
+  if (trace_host) fprintf(stderr, "[tadev summa rank %d] host: everything enqueued at %.3f ms\n", ctx->rank, host_ms());
   TADEV_CHECK_CUDA(cudaEventSynchronize(ev_end));
   TADEV_CHECK_CUDA(cudaGetLastError());
   float ms = 0, gemm_ms = 0;
@@ -925,6 +1098,16 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     cudaEventSynchronize(mk.ev);
     cudaEventElapsedTime(&t, ev_start, mk.ev);
     fprintf(stderr, "[tadev summa rank %d] %-9s block %d window %2d  t=%9.3f ms\n", ctx->rank, mk.what, mk.block, mk.window, t);
+  }
+  for (auto& le : list_events) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, le.first, le.second) == cudaSuccess) list_ms += t; else cudaGetLastError();
+  }
+  if (use_tl) {
+    unsigned long long np = 0;
+    int rc = TL.read_counters(&np, &flops);
+    if (rc) return rc;
+    npairs = (int64_t)np;
   }
   R.ok = true;  // all streams were joined on s0 and s0 has drained: plain stream-ordered release
   if (stats) {
@@ -940,6 +1123,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     stats->row_blocks = nb;
     stats->lazy_tiles = lazy_tiles;
     stats->gemm_ms = gemm_ms;
+    stats->list_ms = list_ms;
   }
   return TADEV_OK;
 }

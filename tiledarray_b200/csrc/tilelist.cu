@@ -56,10 +56,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) tl_scan_add_kernel(int32_t* __re
 }
 
 // in-place exclusive scan of data[0..n); *total = sum. tmp: >= ceil(n / 4096) + 1 ints.
-int tl_scan(cudaStream_t s, int32_t* data, int64_t n, int32_t* tmp, int32_t* total) {
+int tl_scan(tadev_ctx* ctx, cudaStream_t s, int32_t* data, int64_t n, int32_t* tmp, int32_t* total) {
   if (n <= 0) return TADEV_OK;
   const int64_t nb = ceil_div64(n, SCAN_BLOCK);
   TADEV_REQUIRE(nb <= SCAN_BLOCK, "device tile-list builder: %lld elements exceed the two-level scan", (long long)n);
+  ctx->launches += nb == 1 ? 1 : 3;
   if (nb == 1) {
     tl_scan_block_kernel<<<1, SCAN_THREADS, 0, s>>>(data, data, total, n);
   } else {
@@ -101,15 +102,16 @@ __global__ void __launch_bounds__(256) tl_count_kernel(const __grid_constant__ T
     const int i = P.r + li * P.Pr, j = P.c + lj * P.Pc;
     int count = 0;
     long long ksum = 0;
-    const bool cnz = (!P.cn || P.cn[(size_t)i * P.Nt + j] >= P.thr) && P.cptr[g] != nullptr;
+    const bool shape_only = P.atab == nullptr;  // tadev_build_tile_lists: lists from the shapes alone
+    const bool cnz = (!P.cn || P.cn[(size_t)i * P.Nt + j] >= P.thr) && (shape_only || P.cptr[g] != nullptr);
     if (cnz) {
       for (int w = 0; w < P.nws; ++w) {
         const int k = P.ksteps[w];
         if (!tl_pair(P, i, j, k)) continue;
         // the panel tables must hold every tile the shapes call non-zero
-        if (!P.atab[(size_t)w * P.nrows + lr].ptr || !P.btab[(size_t)w * P.ncl + lj].ptr) {
-          if (P.an || P.bn) P.counters->pad = 1;  // sparse: inconsistent tables (reported by the driver)
-          continue;                               // dense: the tile is simply not part of this window's panels
+        if (!shape_only && (!P.atab[(size_t)w * P.nrows + lr].ptr || !P.btab[(size_t)w * P.ncl + lj].ptr)) {
+          if (P.an || P.bn) P.counters->error = 1;  // sparse: inconsistent tables (reported by the driver)
+          continue;                                 // dense: the tile is simply not part of this window's panels
         }
         ++count;
         ksum += P.kext[k];
@@ -135,6 +137,22 @@ __global__ void __launch_bounds__(256) tl_count_kernel(const __grid_constant__ T
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) { np += s_np[w]; fl += s_fl[w]; }
     if (np) { atomicAdd(&P.counters->npairs, np); atomicAdd(&P.counters->flops, fl); }
+  }
+}
+
+// pass 2 of tadev_build_tile_lists: the contracted tile index k of every contribution, chained per result tile
+__global__ void __launch_bounds__(256) tl_fill_k_kernel(const __grid_constant__ TlArgs P, int32_t* __restrict__ task_k, int64_t capacity) {
+  const int ng = P.nrows * P.ncl;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng || P.cnt[g] == 0) return;
+  const int lr = g / P.ncl, lj = g % P.ncl;
+  const int i = P.r + (P.li0 + lr) * P.Pr, j = P.c + lj * P.Pc;
+  int64_t t = P.tbegin[g];
+  for (int w = 0; w < P.nws; ++w) {
+    const int k = P.ksteps[w];
+    if (!tl_pair(P, i, j, k)) continue;
+    if (t < capacity) task_k[t] = k;
+    ++t;
   }
 }
 
@@ -295,6 +313,7 @@ int TileListBuilder::init(tadev_ctx* ctx_, cudaStream_t s_, int Pr_, int Pc_, in
   const size_t o_b2l = carve(brow2li.size() * 4), o_c2l = carve(bcol2lj.size() * 4);
   const size_t host_part = off;  // everything above is initialised from the host
   const size_t o_touch = carve(std::max<size_t>(ng, 1));
+  const size_t o_cp = carve(std::max<size_t>(ng, 1) * 8);
   const size_t o_cnt = carve((ng + 1) * 4), o_tb = carve((ng + 1) * 4), o_nb = carve((ng + 1) * 4), o_bp = carve((ng + 1) * 4);
   const size_t o_kf = carve(cap_keys * 4), o_kp = carve(cap_keys * 4), o_st = carve((size_t)(SCAN_BLOCK + 2) * 4);
   const size_t o_gr = carve(std::max<size_t>(ng, 1) * sizeof(tadev_gemm_group));
@@ -326,6 +345,7 @@ int TileListBuilder::init(tadev_ctx* ctx_, cudaStream_t s_, int Pr_, int Pc_, in
   d_brow0 = (int32_t*)(d_base + o_br0); d_bcol0 = (int32_t*)(d_base + o_bc0);
   d_brow2li = (int32_t*)(d_base + o_b2l); d_bcol2lj = (int32_t*)(d_base + o_c2l);
   d_touched = (uint8_t*)(d_base + o_touch);
+  d_cptr = (double**)(d_base + o_cp);
   d_cnt = (int32_t*)(d_base + o_cnt); d_tbegin = (int32_t*)(d_base + o_tb); d_nblk = (int32_t*)(d_base + o_nb); d_bprefix = (int32_t*)(d_base + o_bp);
   d_kflag = (int32_t*)(d_base + o_kf); d_kpos = (int32_t*)(d_base + o_kp); d_scan_tmp = (int32_t*)(d_base + o_st);
   d_groups = (tadev_gemm_group*)(d_base + o_gr);
@@ -341,29 +361,31 @@ void TileListBuilder::destroy() {
 }
 
 int TileListBuilder::build_and_launch(int opA, int opB, double alpha, int li0, int li1, int nws, const int32_t* d_ksteps,
-                                      const TlTile* d_atab, const TlTile* d_btab, bool fast, cudaEvent_t ev_list0,
-                                      cudaEvent_t ev_list1, cudaEvent_t ev_gemm0, cudaEvent_t ev_gemm1) {
+                                      const TlTile* d_atab, const TlTile* d_btab, double* const* d_cptr_staged, bool fast,
+                                      cudaEvent_t ev_list0, cudaEvent_t ev_list1, cudaEvent_t ev_gemm0, cudaEvent_t ev_gemm1) {
   const int nrows = li1 - li0;
   const int ng = nrows * ncl;
   if (ng <= 0 || nws <= 0) return TADEV_OK;
-  TADEV_REQUIRE(d_cptr, "device tile-list builder: result tile table not set");
   if (ev_list0) TADEV_CHECK_CUDA(cudaEventRecord(ev_list0, s));
+  if (d_cptr_staged)
+    TADEV_CHECK_CUDA(cudaMemcpyAsync(d_cptr + (size_t)li0 * ncl, d_cptr_staged, (size_t)ng * 8, cudaMemcpyDeviceToDevice, s));
   // per-launch counters (everything after npairs/flops)
   TADEV_CHECK_CUDA(cudaMemsetAsync(&d_counters->total_items, 0, sizeof(TlCounters) - offsetof(TlCounters, total_items), s));
   TlArgs A{};
   A.nws = nws; A.li0 = li0; A.nrows = nrows; A.ncl = ncl; A.Pr = Pr; A.Pc = Pc; A.r = r; A.c = c; A.Nt = Nt; A.Kt = Kt;
   A.accumulate = accumulate; A.fast = fast ? 1 : 0; A.thr = thr;
   A.ksteps = d_ksteps; A.an = d_an; A.bn = d_bn; A.cn = d_cn; A.mloc = d_mloc; A.nloc = d_nloc; A.kext = d_kext;
-  A.atab = d_atab; A.btab = d_btab; A.cptr = d_cptr; A.touched = d_touched;
+  A.atab = d_atab; A.btab = d_btab; A.cptr = d_cptr + (size_t)li0 * ncl; A.touched = d_touched;
   A.cnt = d_cnt; A.nblk = d_nblk; A.tbegin = d_tbegin; A.groups = d_groups; A.tasks = d_tasks; A.counters = d_counters;
   const unsigned gb = (unsigned)ceil_div64((int64_t)ng + 1, 256);
   tl_count_kernel<<<gb, 256, 0, s>>>(A);
   TADEV_CHECK_CUDA(cudaMemcpyAsync(d_tbegin, d_cnt, (size_t)(ng + 1) * 4, cudaMemcpyDeviceToDevice, s));
   TADEV_CHECK_CUDA(cudaMemcpyAsync(d_bprefix, d_nblk, (size_t)(ng + 1) * 4, cudaMemcpyDeviceToDevice, s));
-  int rc = tl_scan(s, d_tbegin, (int64_t)ng + 1, d_scan_tmp, &d_counters->total_tasks);
-  if (!rc) rc = tl_scan(s, d_bprefix, (int64_t)ng + 1, d_scan_tmp, &d_counters->total_prefix);
+  int rc = tl_scan(ctx, s, d_tbegin, (int64_t)ng + 1, d_scan_tmp, &d_counters->total_tasks);
+  if (!rc) rc = tl_scan(ctx, s, d_bprefix, (int64_t)ng + 1, d_scan_tmp, &d_counters->total_prefix);
   if (rc) return rc;
   tl_fill_kernel<<<gb, 256, 0, s>>>(A);
+  ctx->launches += 2;
   const int rows_blk = h_brow0[li1] - h_brow0[li0];
   const int64_t max_items = (int64_t)rows_blk * total_bcols;
   if (raster && fast) {
@@ -380,15 +402,16 @@ int TileListBuilder::build_and_launch(int opA, int opB, double alpha, int li0, i
     const unsigned kb = (unsigned)ceil_div64(I.nkeys + 1, 256);
     tl_keyflag_kernel<<<kb, 256, 0, s>>>(I);
     TADEV_CHECK_CUDA(cudaMemcpyAsync(d_kpos, d_kflag, (size_t)(I.nkeys + 1) * 4, cudaMemcpyDeviceToDevice, s));
-    rc = tl_scan(s, d_kpos, I.nkeys + 1, d_scan_tmp, &d_counters->total_items);
+    rc = tl_scan(ctx, s, d_kpos, I.nkeys + 1, d_scan_tmp, &d_counters->total_items);
     if (rc) return rc;
     tl_items_kernel<<<kb, 256, 0, s>>>(I, d_kpos);
+    ctx->launches += 2;
   } else if (fast) {
     tl_items_groupmajor_kernel<<<ng, 256, 0, s>>>(ng, d_nblk, d_bprefix, d_groups, d_items);
     tl_copy_total_kernel<<<1, 1, 0, s>>>(d_counters, &d_counters->total_prefix);
+    ctx->launches += 2;
   }
   TADEV_CHECK_CUDA(cudaGetLastError());
-  ctx->launches += 4;
   if (ev_list1) TADEV_CHECK_CUDA(cudaEventRecord(ev_list1, s));
   GemmTimingHook& hook = tadev_gemm_timing_hook();
   hook.before = ev_gemm0; hook.after = ev_gemm1;
@@ -409,7 +432,8 @@ int TileListBuilder::build_and_launch(int opA, int opB, double alpha, int li0, i
 int TileListBuilder::zero_untouched(int li0, int li1) {
   const int ng = (li1 - li0) * ncl;
   if (ng <= 0 || accumulate) return TADEV_OK;
-  tl_zero_untouched_kernel<<<ng, 256, 0, s>>>(li0, li1 - li0, ncl, Pr, Pc, r, c, Nt, thr, d_cn, d_cptr, d_touched, d_mloc, d_nloc);
+  tl_zero_untouched_kernel<<<ng, 256, 0, s>>>(li0, li1 - li0, ncl, Pr, Pc, r, c, Nt, thr, d_cn, d_cptr + (size_t)li0 * ncl, d_touched,
+                                              d_mloc, d_nloc);
   TADEV_CHECK_CUDA(cudaGetLastError());
   ctx->launches++;
   return TADEV_OK;
@@ -420,8 +444,49 @@ int TileListBuilder::read_counters(unsigned long long* npairs, double* flops) {
   TADEV_CHECK_CUDA(cudaMemcpyAsync(&hc, d_counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
   TADEV_CHECK_CUDA(cudaStreamSynchronize(s));
   *npairs = hc.npairs; *flops = hc.flops;
-  TADEV_REQUIRE(hc.pad == 0, "device tile-list builder: a panel table lacks a tile the shapes call non-zero");
+  TADEV_REQUIRE(hc.error == 0, "device tile-list builder: a panel table lacks a tile the shapes call non-zero");
   return TADEV_OK;
 }
 
-int TileListBuilder::set_result_tiles(int, int, double* const*) { return TADEV_OK; }
+// The list kernel of the SUMMA driver as a stand-alone entry (tests, callers that want the lists): multi-step,
+// multi-CTA successor of tadev_build_pairlist.
+extern "C" int tadev_build_tile_lists(tadev_ctx* ctx, tadev_stream s_, int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt,
+                                      const int32_t* d_ksteps, int nsteps, const float* d_a, const float* d_b, const float* d_c,
+                                      float threshold, int32_t* d_group_begin, int32_t* d_task_k, int64_t capacity,
+                                      int32_t* d_ntasks) {
+  TADEV_REQUIRE(ctx, "tadev_build_tile_lists: null ctx");
+  TADEV_REQUIRE(Pr >= 1 && Pc >= 1 && r >= 0 && r < Pr && c >= 0 && c < Pc, "tadev_build_tile_lists: bad grid position");
+  TADEV_REQUIRE(Mt >= 0 && Nt >= 0 && Kt >= 0 && nsteps >= 0 && capacity >= 0, "tadev_build_tile_lists: bad extents");
+  TADEV_REQUIRE(d_group_begin && d_ntasks && (nsteps == 0 || d_ksteps) && (capacity == 0 || d_task_k), "tadev_build_tile_lists: null arrays");
+  cudaStream_t s = (cudaStream_t)s_;
+  const int nrl = r < Mt ? (Mt - r + Pr - 1) / Pr : 0, ncl = c < Nt ? (Nt - c + Pc - 1) / Pc : 0;
+  const int64_t ng64 = (int64_t)nrl * ncl;
+  TADEV_REQUIRE(ng64 + 1 <= (int64_t)SCAN_BLOCK * SCAN_BLOCK, "tadev_build_tile_lists: tile grid too large");
+  const int ng = (int)ng64;
+  // scratch: cnt[ng+1], nblk[ng+1], mloc[nrl], nloc[ncl], kext[Kt] (unit extents: only counts matter), scan tmp, counters
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_cnt = carve((size_t)(ng + 1) * 4), o_nb = carve((size_t)(ng + 1) * 4), o_ml = carve((size_t)std::max(nrl, 1) * 4),
+               o_nl = carve((size_t)std::max(ncl, 1) * 4), o_ke = carve((size_t)std::max(Kt, 1) * 4), o_st = carve((size_t)(SCAN_BLOCK + 2) * 4),
+               o_ct = carve(sizeof(TlCounters));
+  char* base = nullptr;
+  int rc = tadev_alloc(ctx, off, (void**)&base, s_);
+  if (rc) return rc;
+  TADEV_CHECK_CUDA(cudaMemsetAsync(base, 0, off, s));
+  TlArgs A{};
+  A.nws = nsteps; A.li0 = 0; A.nrows = nrl; A.ncl = ncl; A.Pr = Pr; A.Pc = Pc; A.r = r; A.c = c; A.Nt = Nt; A.Kt = Kt; A.thr = threshold;
+  A.ksteps = d_ksteps; A.an = d_a; A.bn = d_b; A.cn = d_c;
+  A.mloc = (int32_t*)(base + o_ml); A.nloc = (int32_t*)(base + o_nl); A.kext = (int32_t*)(base + o_ke);
+  A.cnt = (int32_t*)(base + o_cnt); A.nblk = (int32_t*)(base + o_nb); A.tbegin = d_group_begin;
+  A.counters = (TlCounters*)(base + o_ct);
+  const unsigned gb = (unsigned)ceil_div64((int64_t)ng + 1, 256);
+  tl_count_kernel<<<gb, 256, 0, s>>>(A);
+  TADEV_CHECK_CUDA(cudaMemcpyAsync(d_group_begin, A.cnt, (size_t)(ng + 1) * 4, cudaMemcpyDeviceToDevice, s));
+  rc = tl_scan(ctx, s, d_group_begin, (int64_t)ng + 1, (int32_t*)(base + o_st), d_ntasks);
+  if (!rc && ng > 0) tl_fill_k_kernel<<<gb, 256, 0, s>>>(A, d_task_k, capacity);
+  ctx->launches += 2;
+  cudaError_t e = cudaGetLastError();
+  tadev_free(ctx, base, s_);
+  TADEV_CHECK_CUDA(e);
+  return rc;
+}

@@ -18,6 +18,7 @@ struct TlTile {
 struct TlCounters {       // device-resident, read back by the driver at the end of the contraction
   unsigned long long npairs;
   double flops;
+  unsigned long long error; // sticky: a panel table lacked a tile the shapes call non-zero
   int32_t total_items;    // work items (128x128 blocks) of the current launch
   int32_t total_tasks;
   int32_t sched[2];       // the persistent kernel's work counter and wave-sync counter (zeroed per launch)
@@ -39,7 +40,7 @@ struct TileListBuilder {
   float *d_an = nullptr, *d_bn = nullptr, *d_cn = nullptr;
   int32_t *d_mloc = nullptr, *d_nloc = nullptr, *d_kext = nullptr;
   int32_t *d_brow0 = nullptr, *d_bcol0 = nullptr, *d_brow2li = nullptr, *d_bcol2lj = nullptr;
-  double** d_cptr = nullptr;            // [nrl * ncl] result tile addresses (device-visible), set per row block
+  double** d_cptr = nullptr;            // [nrl * ncl] result tile addresses (owned copy, refreshed per row block)
   uint8_t* d_touched = nullptr;         // [nrl * ncl]
   int32_t *d_cnt = nullptr, *d_tbegin = nullptr, *d_nblk = nullptr, *d_bprefix = nullptr;  // [ngroups + 1]
   int32_t *d_kflag = nullptr, *d_kpos = nullptr, *d_scan_tmp = nullptr;
@@ -55,13 +56,13 @@ struct TileListBuilder {
   int init(tadev_ctx* ctx, cudaStream_t s, int Pr, int Pc, int r, int c, int Mt, int Nt, int Kt, const int64_t* m_ext,
            const int64_t* n_ext, const int64_t* k_ext, const float* a_norms, const float* b_norms, const float* c_norms,
            float thr, int accumulate, size_t max_tasks);
-  // result-tile addresses of local rows [li0, li1) (host array of nrows*ncl device pointers, row-major)
-  int set_result_tiles(int li0, int li1, double* const* h_cptrs);
   // Build the lists of one window and launch the GEMM. d_ksteps: [nws] global k of each step; d_atab: [nws][li1-li0],
-  // d_btab: [nws][ncl] (device, part of a staged block). fast = every operand row is 16-byte aligned (TMA kernel).
+  // d_btab: [nws][ncl] (device, part of a staged block); d_cptr_staged: result-tile addresses of local rows
+  // [li0, li1) ([nrows][ncl], staged with the first window of a row block; nullptr = unchanged).
+  // fast = every operand row is 16-byte aligned (TMA kernel).
   int build_and_launch(int opA, int opB, double alpha, int li0, int li1, int nws, const int32_t* d_ksteps,
-                       const TlTile* d_atab, const TlTile* d_btab, bool fast, cudaEvent_t ev_list0, cudaEvent_t ev_list1,
-                       cudaEvent_t ev_gemm0, cudaEvent_t ev_gemm1);
+                       const TlTile* d_atab, const TlTile* d_btab, double* const* d_cptr_staged, bool fast,
+                       cudaEvent_t ev_list0, cudaEvent_t ev_list1, cudaEvent_t ev_gemm0, cudaEvent_t ev_gemm1);
   // zero-fill result tiles of rows [li0, li1) that no window touched (beta = 0 contractions only)
   int zero_untouched(int li0, int li1);
   int read_counters(unsigned long long* npairs, double* flops);  // synchronises the stream

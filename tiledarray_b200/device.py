@@ -230,13 +230,19 @@ class Device:
         n = len(ptrs)
         if n == 0:
             return np.zeros(0)
-        d_p = self.upload(np.ascontiguousarray(ptrs, dtype=np.uint64), stream)
-        d_s = self.upload(np.ascontiguousarray(elems, dtype=np.int64), stream)
-        d_o = self.alloc(8 * n, stream)
-        check(self.lib.tadev_tile_sqnorms_f64(self.ctx, stream or self.stream, n, d_p.ptr, d_s.ptr, d_o.ptr))
-        out = self.download(d_o, np.float64, (n,), stream)
-        for b in (d_p, d_s, d_o):
-            b.free()
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.uint64)
+        elems = np.ascontiguousarray(elems, dtype=np.int64)
+        out = np.empty(n)
+        for lo in range(0, n, 65535):  # the entry takes at most 65535 tiles per launch
+            hi = min(n, lo + 65535)
+            d_p = self.upload(ptrs[lo:hi], stream)
+            d_s = self.upload(elems[lo:hi], stream)
+            d_o = self.alloc(8 * (hi - lo), stream)
+            check(self.lib.tadev_tile_sqnorms_f64(self.ctx, stream or self.stream, hi - lo, d_p.ptr, d_s.ptr,
+                                                  int(elems[lo:hi].max()), d_o.ptr))
+            out[lo:hi] = self.download(d_o, np.float64, (hi - lo,), stream)
+            for b in (d_p, d_s, d_o):
+                b.free()
         return out
 
     def add_to(self, n: int, result: DeviceBuffer, arg: DeviceBuffer, stream=None) -> None:
@@ -310,6 +316,30 @@ class Device:
             if x:
                 x.free()
         return pi, pj
+
+    def build_tile_lists(self, ksteps: Sequence[int], Pr: int, Pc: int, r: int, c: int, a: Optional[np.ndarray],
+                         b: Optional[np.ndarray], cn: Optional[np.ndarray], Mt: int, Nt: int, Kt: int, threshold: float):
+        """tadev_build_tile_lists: (group_begin [nrl*ncl + 1], task_k [ntasks]) of a window of SUMMA steps."""
+        d_a = self.upload(np.ascontiguousarray(a, dtype=np.float32).ravel()) if a is not None else None
+        d_b = self.upload(np.ascontiguousarray(b, dtype=np.float32).ravel()) if b is not None else None
+        d_c = self.upload(np.ascontiguousarray(cn, dtype=np.float32).ravel()) if cn is not None else None
+        ks = np.ascontiguousarray(ksteps, dtype=np.int32)
+        d_k = self.upload(ks) if len(ks) else None
+        nrl = (Mt - r + Pr - 1) // Pr if r < Mt else 0
+        ncl = (Nt - c + Pc - 1) // Pc if c < Nt else 0
+        ng = nrl * ncl
+        cap = max(1, ng * max(len(ks), 1))
+        d_g, d_t, d_n = self.alloc(4 * (ng + 1)), self.alloc(4 * cap), self.alloc(4)
+        check(self.lib.tadev_build_tile_lists(self.ctx, self.stream, Pr, Pc, r, c, Mt, Nt, Kt, d_k.ptr if d_k else None, len(ks),
+                                              d_a.ptr if d_a else None, d_b.ptr if d_b else None, d_c.ptr if d_c else None,
+                                              threshold, d_g.ptr, d_t.ptr, cap, d_n.ptr))
+        n = int(self.download(d_n, np.int32, (1,))[0])
+        gb = self.download(d_g, np.int32, (ng + 1,))
+        tk = self.download(d_t, np.int32, (cap,))[:n]
+        for x in (d_a, d_b, d_c, d_k, d_g, d_t, d_n):
+            if x:
+                x.free()
+        return gb, tk
 
     # ---- probes ---------------------------------------------------------------------------
     def probe_fp64_peak(self, kind: int = 0, iters: int = 20000):
