@@ -72,6 +72,45 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def measure_gemm_traffic(args, max_launches=20, timeout_s=420):
+    """DRAM bytes per launch of the GEMM kernel, measured IN THIS RUN: a child `ncu` profiles the same command line
+    (one step, no warm-up, no e2e / CPU legs) for dram__bytes_read.sum + dram__bytes_write.sum of up to
+    `max_launches` launches of gemm_grouped_f64_ws_kernel and the mean per launch is reported (counters, not timings:
+    nothing timed under the profiler is used). Returns (bytes_per_launch, note) or (None, why)."""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
+           "-k", "regex:gemm_grouped_f64_ws_kernel", "-c", str(max_launches), "--csv", sys.executable, os.path.abspath(__file__),
+           "--config", args.config, "--steps", "1", "--warmup", "0", "--no-e2e", "--no-cpu", "--no-traffic", "--parity-tiles", "0"]
+    if args.n:
+        cmd += ["--n", str(args.n)]
+    if args.tile:
+        cmd += ["--tile", str(args.tile)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+    except (subprocess.TimeoutExpired, OSError) as ex:
+        return None, f"ncu child failed: {ex}"
+    rows = [ln for ln in out.stdout.splitlines() if ln.startswith('"')]
+    if len(rows) < 2:
+        return None, "ncu produced no counters (profiling not permitted on this box?): " + (out.stderr or out.stdout)[-200:].replace("\n", " ")
+    per_launch = {}
+    rd = csv.DictReader(io.StringIO("\n".join(rows)))
+    for r in rd:
+        try:
+            per_launch[r["ID"]] = per_launch.get(r["ID"], 0.0) + float(r["Metric Value"].replace(",", ""))
+        except (KeyError, ValueError):
+            continue
+    if not per_launch:
+        return None, "could not parse the ncu output"
+    vals = list(per_launch.values())
+    return float(np.mean(vals)), f"mean of {len(vals)} launch(es) profiled by a child ncu in this run (dram__bytes_read.sum + dram__bytes_write.sum)"
+
+
+# ---------------------------------------------------------------------------------------------
 def _cpu_plan(config, n, tile):
     """(label, m_ext, n_ext, k_ext, opA, opB, a_nz, b_nz, c_nz) of the tile-level contraction the reference's CPU path
     executes for `config`: fused tile extents, BLAS op flags as the reference's permutation optimizer picks them (no
@@ -215,6 +254,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the child-ncu DRAM traffic measurement of the GEMM kernel")
     ap.add_argument("--spl", type=int, default=0, help="SUMMA steps per GEMM launch (0 = auto)")
     ap.add_argument("--parity-tiles", type=int, default=16, help="result tiles EVERY rank verifies (sampled elements)")
     args = ap.parse_args()
@@ -307,6 +347,9 @@ def main():
         parity["tile_pairs_expected"] = wl.extra["pairs"]
         parity["ok"] = parity["ok"] and int(npairs) == wl.extra["pairs"]
 
+    # bytes every launch must move at least once: this rank's operand tiles + its result tiles
+    compulsory = sum(x._arena.nbytes for x in (wl.a, wl.b, wl.c) if getattr(x, "_arena", None) is not None)
+
     # ---- the permute kernel alone (config 5: north_star asks for its HBM fraction): one batched launch over this
     # rank's tiles of the left operand, device-timed
     permute_roofline = None
@@ -397,10 +440,14 @@ def main():
         nl = max(1, step_stats.nlaunches)
         k_ms = float(np.mean(gemm_ms)) / nl if np.mean(gemm_ms) > 0 else float(np.mean(kernel_ms)) / nl
         achieved = step_stats.flops / nl / (k_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
-        if os.path.exists(tpath) and size == 1:
-            traffic = json.load(open(tpath)).get(f"{wl.name}")
+        traffic, traffic_note = None, "not measured (multi-GPU run or --no-traffic)"
+        if size == 1 and not args.no_traffic:
+            traffic, traffic_note = measure_gemm_traffic(args)
+            if traffic is None:  # profiling not possible here: fall back to the committed ncu capture of the same config
+                tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+                if os.path.exists(tpath):
+                    traffic = json.load(open(tpath)).get(wl.name)
+                    traffic_note += "; value from profiles/gemm_traffic.json (committed ncu capture)"
         cfg = {"workload": wl.label, "flop_per_step": flops,
                "parallelism": f"SUMMA {wl.grid[0]}x{wl.grid[1]} process grid, 1 process/GPU",
                "l2": "operands per step >> 126 MB L2 (no flush needed)" if wl.name != "C1" else
@@ -415,7 +462,8 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "peak_sustained": peak_sustained, "frac_of_sustained": achieved / peak_sustained,
-                         "traffic": traffic, "kernel": "gemm_grouped_f64_ws_kernel",
+                         "traffic": traffic, "traffic_source": traffic_note,
+                         "compulsory_bytes_per_launch": compulsory / nl if compulsory else None, "kernel": "gemm_grouped_f64_ws_kernel",
                          "peak_source": "DMMA.8x8x4 register-resident issue-rate probe measured in this run "
                                         "(tadev_probe_fp64_peak: burst = best of two 40k-iteration probes, sustained = one "
                                         "400k-iteration probe; MEASURED_PEAKS.json has no FP64 entry)",

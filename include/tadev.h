@@ -316,6 +316,11 @@ typedef struct {
   tadev_tile_provider b_provider;
   void* b_user;
 } tadev_summa_plan;
+#ifndef TADEV_MEM_DEVICE
+#define TADEV_MEM_DEVICE 0
+#define TADEV_MEM_HOST 1 /* pinned host memory; streamed through the GPU by the SUMMA driver */
+#define TADEV_MEM_LAZY 2 /* never stored: tiles generated on the device when needed (tadev_uniform_source) */
+#endif
 #define TADEV_SUMMA_A_ON_HOST 1
 #define TADEV_SUMMA_B_ON_HOST 2
 #define TADEV_SUMMA_C_ON_HOST 4
@@ -334,7 +339,16 @@ typedef struct {
   int32_t rank;
   int32_t perm[16];         /* image form, as tadev_permute */
   const int64_t* extents;   /* [ntable][rank] extents of each source tile (host) */
-  const void* const* src;   /* [ntable] device pointers of the source tiles (host array) */
+  const void* const* src;   /* [ntable] source tiles (host array): device pointers, or pinned host pointers */
+  /* where the source tiles live: TADEV_MEM_DEVICE (permute straight out of them), TADEV_MEM_HOST (each tile is
+   * uploaded into a stream-ordered scratch buffer first) or TADEV_MEM_LAZY (generated into the scratch buffer by
+   * tadev_fill_uniform_f64(lazy_seed, offset = ordinals[index] << 32) first; src may be NULL). This is how a
+   * host-resident or lazy operand that needs an explicit argument permutation is evaluated tile by tile
+   * (the reference's ArrayEvalImpl does the same per tile, dist_eval/array_eval.h:170,330). */
+  int32_t src_memory;
+  int32_t reserved;
+  uint64_t lazy_seed;
+  const int64_t* ordinals;  /* [ntable] tile ordinal in the ORIGINAL tiling (lazy sources) */
 } tadev_permute_source;
 int tadev_provider_permute(void* permute_source, tadev_stream s, int ntiles, const uint64_t* tokens,
                            double* const* d_dst, const size_t* elems);
@@ -365,9 +379,6 @@ int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tadev_summa_st
  * tile_op/batched_contract_reduce.h, SparseShape::gemm_batched): one grouped-GEMM launch, single rank. This is what a
  * TA::DistArray-level binding calls for `c("i,j") = a("i,k") * b("k,j")` (include/tiledarray.hpp,
  * tiledarray_b200/tiledarray.py). */
-#define TADEV_MEM_DEVICE 0
-#define TADEV_MEM_HOST 1 /* pinned host memory; streamed through the GPU by the SUMMA driver */
-#define TADEV_MEM_LAZY 2 /* never stored: tiles generated on the device when needed (tadev_uniform_source) */
 typedef struct {
   int32_t rank;
   int32_t memory;            /* TADEV_MEM_* */

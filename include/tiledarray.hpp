@@ -338,25 +338,32 @@ struct TsrExpr {
   std::string idx;
   MultExpr<A> operator*(const TsrExpr& o) const { return MultExpr<A>{*this, o}; }
   // products: a contraction, or — when every index is shared and kept — the Hadamard product (mult_engine.h)
-  void operator=(const MultExpr<A>& e) { assign_product(e.left, e.right, 1.0, false); }
-  void operator=(const ScalMultExpr<A>& e) { assign_product(e.expr.left, e.expr.right, e.factor, false); }
-  void operator+=(const MultExpr<A>& e) { assign_product(e.left, e.right, 1.0, true); }
-  void operator+=(const ScalMultExpr<A>& e) { assign_product(e.expr.left, e.expr.right, e.factor, true); }
+  void operator=(const MultExpr<A>& e) { assign_product(e.left, e.right, 1.0, false, e.mask); }
+  void operator=(const ScalMultExpr<A>& e) { assign_product(e.expr.left, e.expr.right, e.factor, false, e.expr.mask); }
+  void operator+=(const MultExpr<A>& e) { assign_product(e.left, e.right, 1.0, true, e.mask); }
+  void operator+=(const ScalMultExpr<A>& e) { assign_product(e.expr.left, e.expr.right, e.factor, true, e.expr.mask); }
   // sums, scaling, copy / permutation (add_engine.h, subt_engine.h, scal_engine.h)
   void operator=(const AddExpr<A>& e) { array->assign_elementwise(idx, TADEV_EW_AXPBY, e.l.f, e.l.t, e.r.f, &e.r.t); }
   void operator=(const ScalTsrExpr<A>& e) { array->assign_elementwise(idx, TADEV_EW_AXPBY, e.f, e.t, 0.0, nullptr); }
   void operator=(const TsrExpr& e) { array->assign_elementwise(idx, TADEV_EW_AXPBY, 1.0, e, 0.0, nullptr); }
 
  private:
-  void assign_product(const TsrExpr& l, const TsrExpr& r, double factor, bool accumulate) {
+  void assign_product(const TsrExpr& l, const TsrExpr& r, double factor, bool accumulate, const typename A::shape_type* mask) {
     if (detail::same_index_set(l.idx, r.idx) && detail::same_index_set(l.idx, idx)) {
       TA_TADEV_ASSERT(!accumulate, "+= of a Hadamard product is not implemented");
+      TA_TADEV_ASSERT(!mask, "set_shape is implemented for contractions only");
       array->assign_elementwise(idx, TADEV_EW_MULT, factor, l, 1.0, &r);
-    } else array->assign_contraction(idx, l, r, factor, accumulate);
+    } else array->assign_contraction(idx, l, r, factor, accumulate, mask);
   }
 };
 template <typename A>
-struct MultExpr { TsrExpr<A> left, right; };
+struct MultExpr {
+  TsrExpr<A> left, right;
+  const typename A::shape_type* mask = nullptr;
+  // (a("m,k") * b("k,n")).set_shape(shape): Expr::set_shape (expressions/expr.h:116) — the result shape is masked by
+  // `shape` after ContEngine::make_shape (cont_engine.h:526-528); `shape` must outlive the assignment
+  MultExpr& set_shape(const typename A::shape_type& shape) { mask = &shape; return *this; }
+};
 template <typename A>
 struct ScalMultExpr { MultExpr<A> expr; double factor; };
 template <typename A>
@@ -556,14 +563,21 @@ class DistArray {
   }
 
   // c(target) (+)= factor * left * right — ExprEngine hand-off (expr.h:378 eval_to)
-  void assign_contraction(const std::string& target, const TsrExpr<DistArray>& l, const TsrExpr<DistArray>& r, double factor, bool accumulate) {
+  void assign_contraction(const std::string& target, const TsrExpr<DistArray>& l, const TsrExpr<DistArray>& r, double factor, bool accumulate,
+                          const shape_type* mask = nullptr) {
     DistArray &A = *l.array, &B = *r.array;
     TA_TADEV_ASSERT(A.st_ && B.st_, "contraction: uninitialized argument");
     World& w = A.world();
     A.allocate_(); B.allocate_();
     Desc da(A), db(B);
     tadev_contraction* eng = nullptr;
-    check(tadev_contraction_create(w.ctx(), target.c_str(), l.idx.c_str(), r.idx.c_str(), &da.d, &db.d, factor, &ContractionOptions::get(), &eng));
+    tadev_contract_options opt = ContractionOptions::get();
+    if (mask) {
+      TA_TADEV_ASSERT(is_sparse && !mask->empty(), "set_shape: a result mask needs the sparse policy and a non-empty shape");
+      opt.mask_norms = mask->data().data();
+      opt.mask_threshold = shape_type::threshold();
+    }
+    check(tadev_contraction_create(w.ctx(), target.c_str(), l.idx.c_str(), r.idx.c_str(), &da.d, &db.d, factor, &opt, &eng));
     std::shared_ptr<tadev_contraction> guard(eng, [](tadev_contraction* e) { tadev_contraction_destroy(e); });
     tadev_contraction_info info;
     check(tadev_contraction_info_get(eng, &info));
@@ -572,16 +586,22 @@ class DistArray {
     TA_TADEV_ASSERT(mem != Lazy, "the result of a contraction cannot be a lazy array");
     std::shared_ptr<State> ns;
     if (accumulate) {
-      TA_TADEV_ASSERT(st_ && st_->arena && st_->trange == tr && st_->arena_elems >= info.arena_elems, "c += a*b: the existing result must have the tiling and tile set of the product");
-      for (int64_t t = 0; t < info.nlocal; ++t) TA_TADEV_ASSERT(st_->tiles[info.ordinals[t]] != nullptr, "c += a*b: the existing result lacks a tile of the product");
-      ns = st_;
+      // the product is added into the EXISTING tiles through their own pointers (whatever the arena layout is)
+      TA_TADEV_ASSERT(st_ && st_->arena && st_->trange == tr, "c += a*b: the existing result must have the tiling of the product");
+      std::vector<void*> tiles((size_t)info.nlocal, nullptr);
+      for (int64_t t = 0; t < info.nlocal; ++t) {
+        tiles[(size_t)t] = st_->tiles[info.ordinals[t]];
+        TA_TADEV_ASSERT(tiles[(size_t)t] != nullptr, "c += a*b: the existing result lacks a tile of the product");
+      }
+      check(tadev_contraction_eval_tiles(eng, tiles.data(), mem, 1, &ContractionOptions::last_stats()));
+      return;
     } else {
       TA_TADEV_ASSERT(!st_ || st_->trange.rank() == 0 || st_->trange == tr || st_->tiles.empty(), "result array tiling does not match the expression");
       if (this != &A && this != &B) st_.reset();  // give the old result back to the pool before allocating the new one
       ns = adopt_structure_(w, info, mem);
       ns->owner = [guard](int64_t ord) { int o = 0; check(tadev_contraction_owner(guard.get(), ord, &o)); return o; };
     }
-    check(tadev_contraction_eval(eng, ns->arena, mem, accumulate ? 1 : 0, &ContractionOptions::last_stats()));
+    check(tadev_contraction_eval(eng, ns->arena, mem, 0, &ContractionOptions::last_stats()));
     st_ = ns;
   }
 

@@ -1,11 +1,13 @@
 set -x
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511"
-nvidia-smi topo -m > gpurun_out/r02_topo.txt 2>&1
-TADEV_SUMMA_TRACE=1 $TR bench.py --gpus 4 --steps 2 --warmup 1 --no-cpu > gpurun_out/r02_n4_base.json 2> gpurun_out/r02_n4_base_trace.log
-TADEV_SM_RESERVE=2 $TR bench.py --gpus 4 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02_n4_res2.json 2> gpurun_out/r02_n4_res2.err
-TADEV_SM_RESERVE=1 $TR bench.py --gpus 4 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02_n4_res1.json 2> gpurun_out/r02_n4_res1.err
-$TR bench.py --gpus 4 --steps 2 --warmup 1 --no-cpu --no-e2e --spl 8 > gpurun_out/r02_n4_spl8.json 2> gpurun_out/r02_n4_spl8.err
-TADEV_SM_RESERVE=2 $TR bench.py --gpus 4 --steps 2 --warmup 1 --no-cpu --no-e2e --spl 8 > gpurun_out/r02_n4_spl8_res2.json 2> gpurun_out/r02_n4_spl8_res2.err
-TADEV_SM_RESERVE=0 $TR bench.py --gpus 4 --steps 2 --warmup 1 --no-cpu --no-e2e --spl 8 > gpurun_out/r02_n4_spl8_res0.json 2> gpurun_out/r02_n4_spl8_res0.err
-tail -n 3 gpurun_out/r02_n4_*.json
+python -m pytest tests -q -m gpu -x > gpurun_out/r02d_pytest_gpu.log 2>&1; tail -12 gpurun_out/r02d_pytest_gpu.log
+LD_LIBRARY_PATH=tiledarray_b200 tests/cpp/build/test_tile_plugin 2>&1 | tail -4
+for c in C1 C2 C3; do
+  timeout 900 python bench.py --config $c > gpurun_out/r02d_bench_$c.json 2> gpurun_out/r02d_bench_$c.err; tail -c 300 gpurun_out/r02d_bench_$c.err
+done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_C2.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-traffic > gpurun_out/r02_launches_C2.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_C3.csv python bench.py --config C3 --steps 2 --warmup 1 --no-e2e --no-cpu --no-traffic > gpurun_out/r02_launches_C3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_grouped_f64_ws -c 1 -o gpurun_out/r02_gemm_C3 python bench.py --config C3 --steps 1 --warmup 0 --no-e2e --no-cpu --no-traffic --parity-tiles 0 > gpurun_out/r02_gemm_C3_ncu.log 2>&1
+ncu --set full --clock-control none -k regex:tl_ -c 12 -o gpurun_out/r02_tilelist_C3 python bench.py --config C3 --steps 1 --warmup 0 --no-e2e --no-cpu --no-traffic --parity-tiles 0 > gpurun_out/r02_tilelist_C3_ncu.log 2>&1
+ls -la gpurun_out/*.ncu-rep
+grep -h '^{' gpurun_out/r02d_bench_C*.json | cut -c1-200

@@ -265,6 +265,41 @@ int main(int argc, char** argv) {
     ok = true;
     for (size_t i = 0; i < S1.size(); ++i) ok = ok && S2[i] == 2 * S1[i];
     CHECK(ok);
+
+    // c("m,n") = (a("m,k") * b("k,n")).set_shape(mask): the expression of examples/gemm/ta_sparse.cpp:190. Result tiles
+    // the mask calls zero are absent; the others equal the plain product; += then adds into a DIFFERENT array (its own
+    // tile pointers: an array whose arena was laid out by another expression)
+    TA::TSpArrayD prod, masked;
+    prod("m,n") = sa("m,k") * sa("k,n");
+    TA::Tensor<float> mnorms(tadev::Range{4, 4}, 0.0f);
+    for (int64_t o = 0; o < 16; ++o) mnorms[(size_t)o] = (o % 2) ? 7.0f : 0.0f;
+    const TA::SparseShape<float> mask(world, mnorms, tr);
+    masked("m,n") = (sa("m,k") * sa("k,n")).set_shape(mask);
+    const auto P = to_host(prod), M = to_host(masked);
+    ok = true;
+    for (int64_t o = 0; o < 16; ++o) {
+      CHECK(masked.is_zero(o) == (prod.is_zero(o) || mask.is_zero(o)));
+      const auto ext = tr.tile_extent(o);
+      const int64_t ti = o / 4, tj = o % 4;
+      for (int64_t x = 0; x < ext[0]; ++x)
+        for (int64_t y = 0; y < ext[1]; ++y) {
+          const size_t at = (size_t)((ti * 8 + x) * 32 + tj * 8 + y);
+          ok = ok && M[at] == (masked.is_zero(o) ? 0.0 : P[at]);
+        }
+    }
+    CHECK(ok);
+    TA::TSpArrayD acc;
+    acc("n,m") = 1.0 * sa("m,n");                       // laid out by a permuting element-wise expression
+    acc("n,m") += (sa("m,k") * sa("k,n")).set_shape(acc.shape());  // masked by its own shape: every product tile exists in acc
+    const auto ACC = to_host(acc), SA = to_host(sa);
+    ok = true;
+    for (int i = 0; i < 32; ++i)
+      for (int j = 0; j < 32; ++j) {
+        const int64_t o = (int64_t)(j / 8) * 4 + i / 8;  // tile of acc (n = j, m = i)
+        const double want = acc.is_zero(o) ? 0.0 : SA[(size_t)i * 32 + j] + P[(size_t)i * 32 + j];
+        ok = ok && ACC[(size_t)j * 32 + i] == want;
+      }
+    CHECK(ok);
   }
 
   TA::finalize();

@@ -670,3 +670,51 @@ def test_device_lists_match_host_lists(world, case, monkeypatch):
     assert out["0"][1:] == out["1"][1:]
     for x in (a, b):
         x.release()
+
+
+@pytest.mark.parametrize("where", ["host", "lazy", "mixed"])
+def test_cont_permuted_host_and_lazy_operands(world, where):
+    """Operands that are NOT device-resident and need an explicit argument permutation (BASELINE config 5's index
+    pattern): host-resident tiles are uploaded and permuted, lazy tiles generated and permuted, tile by tile when a
+    SUMMA window asks for them (what ArrayEvalImpl does per tile, dist_eval/array_eval.h:170,330); also a
+    host-resident result that needs a result permutation."""
+    from tests import util_rng
+    s, v = TiledRange1(0, 2, 6), TiledRange1(0, 8, 16, 20)
+    trA, trB = _tr(s, s, v, v), _tr(s, v, s, v)
+
+    def host_full(tr, seed):
+        full = np.zeros(tr.elements_shape)
+        for o in range(tr.ntiles):
+            idx = tr.tile_index(o)
+            ext = tr.tile_extent(idx)
+            full[tr.tile_slices(idx)] = util_rng.tile_fill(o, int(np.prod(ext)), seed).reshape(ext)
+        return full
+
+    A, B = host_full(trA, 41), host_full(trB, 42)
+    if where == "host":
+        a = DistArray(world, trA, memory="host").fill_random(41)
+        b = DistArray(world, trB, memory="host").fill_random(42)
+    elif where == "lazy":
+        a = DistArray(world, trA, memory="lazy", lazy_seed=41)
+        b = DistArray(world, trB, memory="lazy", lazy_seed=42)
+    else:
+        a = DistArray(world, trA, memory="host").fill_random(41)
+        b = DistArray(world, trB, memory="lazy", lazy_seed=42)
+    ref = np.einsum("ikac,jckb->iajb", A, B)
+    for spl in (0, 1):
+        ContEngine.steps_per_launch = spl
+        try:
+            c = DistArray(world, _tr(s, v, s, v))
+            c["i,a,j,b"] = a["i,k,a,c"] * b["j,c,k,b"]
+            assert O.rel_frobenius(c.to_numpy(), ref) < TOL, (where, spl)
+            assert ContEngine.last_stats.lazy_tiles > 0
+            c.release()
+            # host-resident result in another index order: the product is permuted on the device, then copied back
+            ch = DistArray(world, _tr(v, s, v, s), memory="host")
+            ch["a,i,b,j"] = a["i,k,a,c"] * b["j,c,k,b"]
+            assert O.rel_frobenius(ch.to_numpy(), ref.transpose(1, 0, 3, 2)) < TOL, (where, spl)
+            ch.release()
+        finally:
+            ContEngine.steps_per_launch = 0
+    for x in (a, b):
+        x.release()

@@ -94,7 +94,9 @@ class UniformSourceC(C.Structure):
 
 class PermuteSourceC(C.Structure):
     _fields_ = [("ctx", C.c_void_p), ("rank", C.c_int32), ("perm", C.c_int32 * 16),
-                ("extents", C.POINTER(C.c_int64)), ("src", C.POINTER(C.c_void_p))]
+                ("extents", C.POINTER(C.c_int64)), ("src", C.POINTER(C.c_void_p)),
+                ("src_memory", C.c_int32), ("reserved", C.c_int32), ("lazy_seed", C.c_uint64),
+                ("ordinals", C.POINTER(C.c_int64))]
 
 
 class SummaStatsC(C.Structure):

@@ -299,10 +299,8 @@ static int plan_structure(tadev_contraction* Ep, int nranks, const char* target,
   if ((rc = copy_operand(E->swapped ? right : left, E->L, "tadev_contraction_create(left)", need_tiles))) return rc;
   if ((rc = copy_operand(E->swapped ? left : right, E->R, "tadev_contraction_create(right)", need_tiles))) return rc;
   TADEV_REQUIRE(E->L.tr.rank() == P.left_rank && E->R.tr.rank() == P.right_rank, "index list rank does not match the array");
-  TADEV_REQUIRE(E->L.d.memory != TADEV_MEM_HOST || P.perm_left[0] < 0, "host-resident left operand needs an explicit permutation: not supported");
-  TADEV_REQUIRE(E->R.d.memory != TADEV_MEM_HOST || P.perm_right[0] < 0, "host-resident right operand needs an explicit permutation: not supported");
-  TADEV_REQUIRE(E->L.d.memory != TADEV_MEM_LAZY || P.perm_left[0] < 0, "a lazy operand that needs an explicit permutation is not supported");
-  TADEV_REQUIRE(E->R.d.memory != TADEV_MEM_LAZY || P.perm_right[0] < 0, "a lazy operand that needs an explicit permutation is not supported");
+  // (host-resident and lazy operands that need an explicit permutation are permuted tile by tile when a SUMMA window
+  // asks for them: build_view configures the permute provider for their memory kind)
   build_operand_structure(E->L, P.perm_left, P.left_rank);
   build_operand_structure(E->R, P.perm_right, P.right_rank);
 
@@ -559,6 +557,7 @@ struct View {
   tadev_permute_source psrc{};
   std::vector<int64_t> p_ext;      // [ntok][rank]
   std::vector<const void*> p_src;  // [ntok]
+  std::vector<int64_t> p_ord;      // [ntok] original tile ordinals (lazy sources)
   double* tmp_arena = nullptr;     // up-front permuted copy
   void* user() { return provider == tadev_provider_uniform ? (void*)&usrc : (void*)&psrc; }
 };
@@ -643,13 +642,21 @@ int build_view(tadev_contraction* E, Operand& o, bool is_left, View& v, float* p
     for (int i = 0; i < R; ++i) pidx[o.perm[i]] = idx[i];
     return ravel(pidx, pshape);
   };
-  if (o.d.memory == TADEV_MEM_LAZY) {
+  // a lazy tile can be generated anywhere: it is "local" exactly where SUMMA's cyclic maps want it, whatever table
+  // the caller passed (this is the redistribution of a lazy operand: none is needed)
+  auto lazy_local = [&](int64_t po) {
+    if (ctx->nranks == 1) return true;
+    const size_t pos = fused_pos(po, op_n, rows, cols);
+    const int64_t fr = (int64_t)pos / cols, fc = (int64_t)pos % cols;
+    return (int)((fr % E->Pr) * E->Pc + fc % E->Pc) == ctx->rank;
+  };
+  if (o.d.memory == TADEV_MEM_LAZY && o.perm.empty()) {
     v.lazy = true;
     v.provider = tadev_provider_uniform;
     v.usrc.ctx = ctx; v.usrc.seed = o.d.lazy_seed;
     for (int64_t ord = 0; ord < n; ++ord) {
       if (!o.dense() && o.norms[ord] < thr) continue;
-      if (!o.tiles.empty() && !o.tiles[ord]) continue;  // not local
+      if (!lazy_local(ord)) continue;
       v.table[fused_pos(ord, op_n, rows, cols)] = reinterpret_cast<const double*>((uintptr_t)(ord + 1));
     }
     return TADEV_OK;
@@ -663,22 +670,29 @@ int build_view(tadev_contraction* E, Operand& o, bool is_left, View& v, float* p
   std::vector<int64_t> ords, exts;
   int64_t bytes = 0;
   for (int64_t ord = 0; ord < n; ++ord) {
-    if (!o.tiles[ord]) continue;
+    if (o.d.memory == TADEV_MEM_LAZY) {
+      if ((!o.dense() && o.norms[ord] < thr) || !lazy_local(permuted_ordinal(ord))) continue;
+    } else if (!o.tiles[ord]) continue;
     ords.push_back(ord);
     unravel(ord, tshape, idx);
     int64_t vol = 1;
     for (int d = 0; d < R; ++d) { exts.push_back(o.tr.ext(d, idx[d])); vol *= exts.back(); }
     bytes += vol * 8;
   }
-  bool stream = !E->general && (E->opt.stream_permutes > 0 || (E->opt.stream_permutes < 0 && bytes > E->opt.stream_permute_bytes));
+  // host-resident and lazy sources are always permuted per SUMMA window (there is no device copy to permute up front)
+  bool stream = !E->general && (o.d.memory != TADEV_MEM_DEVICE || E->opt.stream_permutes > 0 ||
+                                (E->opt.stream_permutes < 0 && bytes > E->opt.stream_permute_bytes));
+  TADEV_REQUIRE(o.d.memory == TADEV_MEM_DEVICE || stream, "general products take device-resident arrays");
   if (stream) {
     v.lazy = true;
     v.provider = tadev_provider_permute;
     v.p_ext = exts;
-    for (int64_t ord : ords) v.p_src.push_back(o.tiles[ord]);
+    v.p_ord = ords;
+    if (o.d.memory != TADEV_MEM_LAZY) for (int64_t ord : ords) v.p_src.push_back(o.tiles[ord]);
     v.psrc.ctx = ctx; v.psrc.rank = R;
     for (int i = 0; i < R; ++i) v.psrc.perm[i] = o.perm[i];
-    v.psrc.extents = v.p_ext.data(); v.psrc.src = v.p_src.data();
+    v.psrc.extents = v.p_ext.data(); v.psrc.src = v.p_src.empty() ? nullptr : v.p_src.data();
+    v.psrc.src_memory = o.d.memory; v.psrc.lazy_seed = o.d.lazy_seed; v.psrc.ordinals = v.p_ord.data();
     for (size_t t = 0; t < ords.size(); ++t)
       v.table[fused_pos(permuted_ordinal(ords[t]), op_n, rows, cols)] = reinterpret_cast<const double*>((uintptr_t)(t + 1));
     return TADEV_OK;
@@ -831,7 +845,7 @@ extern "C" int tadev_contraction_eval_tiles(tadev_contraction* E, void* const* r
     sp.a_tiles = vA.table.data(); sp.b_tiles = vB.table.data(); sp.c_tiles = c_tab.data();
     sp.accumulate = gemm_accumulate;
     sp.depth = E->opt.depth; sp.steps_per_launch = E->opt.steps_per_launch; sp.row_blocks = E->opt.row_blocks;
-    sp.flags = (E->L.d.memory == TADEV_MEM_HOST ? TADEV_SUMMA_A_ON_HOST : 0) | (E->R.d.memory == TADEV_MEM_HOST ? TADEV_SUMMA_B_ON_HOST : 0) |
+    sp.flags = (E->L.d.memory == TADEV_MEM_HOST && !vA.lazy ? TADEV_SUMMA_A_ON_HOST : 0) | (E->R.d.memory == TADEV_MEM_HOST && !vB.lazy ? TADEV_SUMMA_B_ON_HOST : 0) |
                (gemm_memory == TADEV_MEM_HOST ? TADEV_SUMMA_C_ON_HOST : 0) | (vA.lazy ? TADEV_SUMMA_A_LAZY : 0) | (vB.lazy ? TADEV_SUMMA_B_LAZY : 0);
     if (vA.lazy) { sp.a_provider = vA.provider; sp.a_user = vA.user(); }
     if (vB.lazy) { sp.b_provider = vB.provider; sp.b_user = vB.user(); }

@@ -142,15 +142,32 @@ extern "C" int tadev_provider_uniform(void* user, tadev_stream s, int ntiles, co
 extern "C" int tadev_provider_permute(void* user, tadev_stream s, int ntiles, const uint64_t* tokens,
                                       double* const* d_dst, const size_t* elems) {
   const tadev_permute_source* src = static_cast<const tadev_permute_source*>(user);
-  TADEV_REQUIRE(src && src->ctx && src->extents && src->src && src->rank >= 0 && src->rank <= 16, "tadev_provider_permute: bad source");
+  TADEV_REQUIRE(src && src->ctx && src->extents && src->rank >= 0 && src->rank <= 16, "tadev_provider_permute: bad source");
+  TADEV_REQUIRE(src->src_memory == TADEV_MEM_LAZY ? src->ordinals != nullptr : src->src != nullptr, "tadev_provider_permute: bad source tables");
   TADEV_REQUIRE(ntiles == 0 || (tokens && d_dst && elems), "tadev_provider_permute: null");
   const int R = src->rank;
+  // host-resident / lazy sources are first brought into a stream-ordered scratch buffer (one per call)
+  double* scratch = nullptr;
+  std::vector<size_t> soff((size_t)ntiles, 0);
+  if (src->src_memory != TADEV_MEM_DEVICE && ntiles > 0) {
+    size_t tot = 0;
+    for (int n = 0; n < ntiles; ++n) { soff[n] = tot; tot += (elems[n] + 1) & ~size_t(1); }
+    int rc = tadev_alloc(src->ctx, std::max<size_t>(tot, 2) * 8, (void**)&scratch, s);
+    if (rc) return rc;
+    for (int n = 0; n < ntiles && !rc; ++n) {
+      if (tokens[n] == 0) { rc = TADEV_EINVAL; tadev_set_error("tadev_provider_permute: zero token"); break; }
+      if (src->src_memory == TADEV_MEM_HOST) rc = tadev_memcpy_h2d(src->ctx, scratch + soff[n], src->src[tokens[n] - 1], elems[n] * 8, s);
+      else rc = tadev_fill_uniform_f64(src->ctx, s, scratch + soff[n], elems[n], src->lazy_seed, (uint64_t)src->ordinals[tokens[n] - 1] << 32);
+    }
+    if (rc) { tadev_free(src->ctx, scratch, s); return rc; }
+  }
   std::vector<char> done((size_t)ntiles, 0);
   std::vector<const void*> ins;
   std::vector<void*> outs;
-  for (int n = 0; n < ntiles; ++n) {
+  int rc = TADEV_OK;
+  for (int n = 0; n < ntiles && !rc; ++n) {
     if (done[n]) continue;
-    TADEV_REQUIRE(tokens[n] != 0, "tadev_provider_permute: zero token");
+    if (tokens[n] == 0) { tadev_set_error("tadev_provider_permute: zero token"); rc = TADEV_EINVAL; break; }
     const int64_t* ext = src->extents + (size_t)(tokens[n] - 1) * R;
     ins.clear(); outs.clear();
     for (int q = n; q < ntiles; ++q) {
@@ -159,15 +176,15 @@ extern "C" int tadev_provider_permute(void* user, tadev_stream s, int ntiles, co
       if (q != n && memcmp(eq, ext, sizeof(int64_t) * R) != 0) continue;
       size_t vol = 1;
       for (int d = 0; d < R; ++d) vol *= (size_t)eq[d];
-      TADEV_REQUIRE(vol == elems[q], "tadev_provider_permute: tile %d has %zu elements, the driver expects %zu", q, vol, elems[q]);
-      ins.push_back(src->src[tokens[q] - 1]);
+      if (vol != elems[q]) { tadev_set_error("tadev_provider_permute: tile %d has %zu elements, the driver expects %zu", q, vol, elems[q]); rc = TADEV_EINVAL; break; }
+      ins.push_back(scratch ? (const void*)(scratch + soff[q]) : src->src[tokens[q] - 1]);
       outs.push_back(d_dst[q]);
       done[q] = 1;
     }
-    int rc = tadev_permute_batched(src->ctx, s, R, ext, src->perm, 8, (int)ins.size(), ins.data(), outs.data());
-    if (rc) return rc;
+    if (!rc) rc = tadev_permute_batched(src->ctx, s, R, ext, src->perm, 8, (int)ins.size(), ins.data(), outs.data());
   }
-  return TADEV_OK;
+  if (scratch) tadev_free(src->ctx, scratch, s);
+  return rc;
 }
 
 namespace {
