@@ -1,7 +1,7 @@
 """Worker of tests/test_gpu_multi.py::test_baseline_configs_multi_rank: miniatures of BASELINE configs 3, 4 and 5 on
 N GPUs, operands created by tiledarray.contraction_arrays (already in SUMMA's distribution: no redistribution), every
 local result tile compared in full with a host einsum of the regenerated operands.
-usage: _multi_gpu_worker_configs.py <case>     case in {c3, c3m, c4, c5, c5s}
+usage: _multi_gpu_worker_configs.py <case>     case in {c3, c3m, c4, c5, c5s, general, generalp}
 """
 import os
 import sys
@@ -57,6 +57,14 @@ def main():
         trA, trB, trC = TiledRange([v1, v1, o1, o1]), TiledRange([v1, v1, v1, v1]), TiledRange([v1, v1, o1, o1])
         target, lidx, ridx = "a,b,i,j", "c,d,i,j", "a,b,c,d"
         lazy = (None, 808)
+    elif case in ("general", "generalp"):  # fused (batch) index b: one SUMMA per slab and batch element on the shared grid
+        bt, d1, d2 = TiledRange1(0, 2, 5), TiledRange1.make_uniform(24, 8), TiledRange1(0, 6, 16, 20)
+        if case == "general":
+            trA, trB, trC = TiledRange([bt, d1, d2]), TiledRange([bt, d2, d1]), TiledRange([bt, d1, d1])
+            target, lidx, ridx = "b,i,j", "b,i,k", "b,k,j"
+        else:  # non-canonical argument layouts: permuted first
+            trA, trB, trC = TiledRange([d1, d2, bt]), TiledRange([d1, d2, bt]), TiledRange([bt, d1, d1])
+            target, lidx, ridx = "b,i,j", "i,k,b", "j,k,b"
     else:  # c5 / c5s: both operands explicitly permuted (up front / streamed per SUMMA window)
         s1, b1 = TiledRange1.make_uniform(8, 2), TiledRange1.make_uniform(24, 8)
         trA, trB, trC = TiledRange([s1, s1, b1, b1]), TiledRange([s1, b1, s1, b1]), TiledRange([s1, b1, s1, b1])

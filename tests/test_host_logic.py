@@ -392,3 +392,15 @@ def test_contraction_layout_named_configs():
         row = idx[rt[0]] * ntl[rt[1]] + idx[rt[1]]
         col = idx[rt[2]] * ntl[rt[3]] + idx[rt[3]]
         assert (rr[o], rc[o]) == (row, col)
+
+
+def test_tiledarray_shim_type_checks():
+    """include/tadev_tiledarray_shim.hpp (TA::Tile<tadevTensor>, is_device_tile, madness::archive load/store, array
+    conversions, SummaTadev : DistEvalImpl) is written against TiledArray's own headers; here it is type-checked with
+    every template instantiated against the facsimile declarations of the reference interfaces
+    (tests/cpp/ta_facsimile/README.md)."""
+    import subprocess
+    out = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"),
+                          "-I", os.path.join(ROOT, "tests", "cpp", "ta_facsimile"),
+                          os.path.join(ROOT, "tests", "cpp", "test_shim_syntax.cpp")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]

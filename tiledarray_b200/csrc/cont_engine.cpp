@@ -315,7 +315,7 @@ static int plan_structure(tadev_contraction* Ep, int nranks, const char* target,
     // ranges in the canonical layouts: left (H, outer, K), right (H, K, outer)
     const int nh = E->nh;
     TADEV_REQUIRE(E->L.d.memory == TADEV_MEM_DEVICE && E->R.d.memory == TADEV_MEM_DEVICE, "general products take device-resident arrays");
-    TADEV_REQUIRE(nranks == 1, "general (fused-index) products are evaluated on one rank in this version");
+    (void)nranks;  // multi-rank general products: every fused slab is a SUMMA on the shared 2-d grid (see eval)
     E->lo[0] = nh; E->lo[1] = E->li[0] = lr - nc; E->li[1] = lr;
     E->ri[0] = nh; E->ri[1] = E->ro[0] = nh + nc; E->ro[1] = rr;
     for (int d = 0; d < nh; ++d) TADEV_REQUIRE(trA.b[d] == trB.b[d], "general product: the fused tiled ranges are not congruent");
@@ -374,7 +374,9 @@ extern "C" int tadev_contraction_layout(const char* target, const char* left_idx
     int32_t* fcol = user_left ? left_fcol : right_fcol;
     if (!frow || !fcol) continue;
     const bool op_n = (side == 0 ? E->plan.opA : E->plan.opB) == TADEV_OP_N;
-    const int64_t rows = (int64_t)(E->general ? E->Ht : 1) * (side == 0 ? E->Mt : E->Kt), cols = side == 0 ? E->Kt : E->Nt;
+    // general products: the fused slabs share ONE 2-d grid, a tile's owner does not depend on its slab
+    // (contraction_eval.h:96-104: "nh_ independent SUMMA slabs sharing one process grid"): positions are slab-local
+    const int64_t rows = side == 0 ? E->Mt : E->Kt, cols = side == 0 ? E->Kt : E->Nt;
     const int R = o.tr.rank();
     const std::vector<int64_t> tshape = o.tr.tiles_shape(), pshape = o.ptr.tiles_shape();
     std::vector<int64_t> idx, pidx(R);
@@ -385,6 +387,7 @@ extern "C" int tadev_contraction_layout(const char* target, const char* left_idx
         for (int i = 0; i < R; ++i) pidx[o.perm[i]] = idx[i];
         po = ravel(pidx, pshape);
       }
+      if (E->general) po %= rows * cols;
       const int64_t pos = op_n ? po : (po % rows) * cols + po / rows;  // == fused_pos()
       frow[ord] = (int32_t)(pos / cols); fcol[ord] = (int32_t)(pos % cols);
     }
@@ -532,7 +535,7 @@ extern "C" int tadev_contraction_owner(const tadev_contraction* E, int64_t targe
   if (E->perm_res.empty()) gidx = tidx;
   else for (size_t a = 0; a < tidx.size(); ++a) gidx[a] = tidx[E->perm_res[a]];
   const int64_t go = ravel(gidx, E->tr_gemm.tiles_shape());
-  *owner = (int)(((go / E->Nt) % E->Pr) * E->Pc + (go % E->Nt) % E->Pc);
+  *owner = (int)((((go / E->Nt) % E->Mt) % E->Pr) * E->Pc + (go % E->Nt) % E->Pc);  // (% Mt: the owner does not depend on the fused slab)
   return TADEV_OK;
 }
 
@@ -594,7 +597,7 @@ int redistribute_operand(tadev_contraction* E, Operand& o, bool is_left) {
     int64_t po = ord;
     unravel(ord, tshape, idx);
     if (!o.perm.empty()) { for (int i = 0; i < R; ++i) pidx[o.perm[i]] = idx[i]; po = ravel(pidx, pshape); }
-    const size_t pos = fused_pos(po, op_n, rows, cols);
+    const size_t pos = fused_pos(E->general ? po % (rows * cols) : po, op_n, rows, cols);  // general: slab-local position
     const int64_t fr = (int64_t)pos / cols, fc = (int64_t)pos % cols;
     need[ord] = (int32_t)((fr % E->Pr) * E->Pc + fc % E->Pc);
     TADEV_REQUIRE(o.owners[ord] >= 0 && o.owners[ord] < ctx->nranks, "redistribution: tile %lld has owner %d", (long long)ord, o.owners[ord]);
@@ -795,7 +798,54 @@ extern "C" int tadev_contraction_eval_tiles(tadev_contraction* E, void* const* r
   const int gemm_accumulate = permuted ? 0 : (accumulate ? 1 : 0);
 
   tadev_summa_stats st{};
-  if (E->general) {
+  if (E->general && ctx->nranks > 1) {
+    // Multi-rank general product: the reference evaluates the nh fused slabs as independent SUMMAs that share one
+    // process grid (contraction_eval.h:96-104, proc_h_ == 1). A tile (nb, m, k) holds nb contiguous row-major
+    // matrices, so batch element e of slab h is an ordinary matrix SUMMA over tile pointers offset by e*m*k: the
+    // driver runs once per (slab, batch element), every rank in the same order. (Panels of one batch element are
+    // strided in their tiles and are packed before they travel; moving whole batched tiles once per slab is the
+    // obvious next step.)
+    TADEV_REQUIRE(gemm_memory == TADEV_MEM_DEVICE, "general products produce device-resident results");
+    const int Mt = E->Mt, Nt = E->Nt, Kt = E->Kt;
+    std::vector<const double*> at((size_t)Mt * Kt), bt((size_t)Kt * Nt);
+    std::vector<double*> ct((size_t)Mt * Nt);
+    for (int h = 0; h < E->Ht && !rc; ++h)
+      for (int64_t e = 0; e < E->h_ext[h] && !rc; ++e) {
+        for (int i = 0; i < Mt; ++i)
+          for (int k = 0; k < Kt; ++k) {
+            const double* p = vA.table[((size_t)h * Mt + i) * Kt + k];
+            at[(size_t)i * Kt + k] = p ? p + e * E->m_ext[i] * E->k_ext[k] : nullptr;
+          }
+        for (int k = 0; k < Kt; ++k)
+          for (int j = 0; j < Nt; ++j) {
+            const double* p = vB.table[((size_t)h * Kt + k) * Nt + j];
+            bt[(size_t)k * Nt + j] = p ? p + e * E->k_ext[k] * E->n_ext[j] : nullptr;
+          }
+        for (int i = 0; i < Mt; ++i)
+          for (int j = 0; j < Nt; ++j) {
+            double* p = c_tab[((size_t)h * Mt + i) * Nt + j];
+            ct[(size_t)i * Nt + j] = p ? p + e * E->m_ext[i] * E->n_ext[j] : nullptr;
+          }
+        tadev_summa_plan sp{};
+        sp.Mt = Mt; sp.Nt = Nt; sp.Kt = Kt;
+        sp.m_ext = E->m_ext.data(); sp.n_ext = E->n_ext.data(); sp.k_ext = E->k_ext.data();
+        sp.opA = TADEV_OP_N; sp.opB = TADEV_OP_N; sp.alpha = E->factor;
+        sp.a_norms = E->sparse ? E->a_n.data() + (size_t)h * Mt * Kt : nullptr;
+        sp.b_norms = E->sparse ? E->b_n.data() + (size_t)h * Kt * Nt : nullptr;
+        sp.c_norms = E->sparse ? E->c_n.data() + (size_t)h * Mt * Nt : nullptr;
+        sp.threshold = E->opt.threshold;
+        sp.a_tiles = at.data(); sp.b_tiles = bt.data(); sp.c_tiles = ct.data();
+        sp.accumulate = gemm_accumulate;
+        sp.depth = E->opt.depth; sp.steps_per_launch = E->opt.steps_per_launch;
+        tadev_summa_stats one{};
+        rc = tadev_summa_f64(ctx, &sp, &one);
+        st.nsteps += one.nsteps; st.nsteps_skipped += one.nsteps_skipped; st.nlaunches += one.nlaunches;
+        st.bcast_bytes += one.bcast_bytes; st.device_ms += one.device_ms; st.gemm_ms += one.gemm_ms; st.list_ms += one.list_ms;
+        st.flops += one.flops;
+        if (e == 0) st.npairs += one.npairs;  // pairs are counted per tile, as on one rank
+      }
+    st.row_blocks = 1;
+  } else if (E->general) {
     // BatchedContractReduce (tile_op/batched_contract_reduce.h) for every result tile of every fused slab,
     // in ONE grouped launch: batch element e of tile (h,i,j) is its own group — C + e*m*n accumulates
     // A(h,i,k)[e] * B(h,k,j)[e] over the contracted tiles k (a tile (nb, m, k) is nb row-major m x k matrices).

@@ -291,7 +291,10 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
   // W = ceil(4096 contracted elements / average k extent), multiplied by the reference's sparse boost
   // 1 - 1.35638 log2((1 - min(sA, 0.9)) (1 - min(sB, 0.9))); D * W <= TA_SUMMA_MAX_DEPTH; D * window bytes <=
   // TA_SUMMA_MAX_MEMORY (same syntax as the reference: "<number> [kB|KiB|MB|MiB|GB|GiB]", at least 100 MiB).
-  X.D = std::max(2, P.depth > 0 ? P.depth : 2);
+  // ring depth: 2 windows in flight (broadcast of n+1 under the GEMM of n); staged operands (host-resident / lazy)
+  // that are also broadcast have three stages per window - upload or generate, broadcast, GEMM - and need 3 slots,
+  // else every other window waits for a slot (8 GPUs, host operands: 12.7 ms per 8.5 ms window with depth 2)
+  X.D = P.depth > 0 ? std::max(2, P.depth) : ((multi && (a_stg || b_stg)) ? 3 : 2);
   size_t kMaxWindowBytes = size_t(5) << 30;
   if (const char* e = getenv("TA_SUMMA_MAX_MEMORY")) {
     char unit[16] = "";
@@ -338,8 +341,12 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
   // communicator must put the same broadcasts into the same group: window boundaries are therefore
   // derived from replicated data only (globally active steps, a byte bound that is the maximum
   // over all grid positions), never from this rank's own compute pattern.
-  std::vector<int> win_of_k(std::max(Kt, 1), 0);
-  {
+  // Two maps: block 0 ramps its windows up (pipeline fill); later row blocks of a host-resident / lazy-operand
+  // contraction start with their first panels already prefetched during the previous block, so they use full-size
+  // windows from the start (the ramp cost ~15 % per block: profiles/r02_trace_C2_n8_e2e_depth2.log).
+  std::vector<int> win_of_k(std::max(Kt, 1), 0), win_of_k_steady(std::max(Kt, 1), 0);
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<int>& wmap = pass == 0 ? win_of_k : win_of_k_steady;
     auto a_nz = [&](int i, int k) { return !P.a_norms || P.a_norms[(size_t)i * Kt + k] >= P.threshold; };
     auto b_nz = [&](int k, int j) { return !P.b_norms || P.b_norms[(size_t)k * Nt + j] >= P.threshold; };
     int nwin = 0, cnt = 0;
@@ -351,7 +358,7 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
       bool any_a = false, any_b = false;
       for (int i = 0; i < Mt; ++i) if (a_nz(i, k)) { any_a = true; per_r[i % Pr] += pad2((size_t)P.m_ext[i] * P.k_ext[k]) * 8; }
       for (int j = 0; j < Nt; ++j) if (b_nz(k, j)) { any_b = true; per_c[j % Pc] += pad2((size_t)P.k_ext[k] * P.n_ext[j]) * 8; }
-      win_of_k[k] = nwin;
+      wmap[k] = nwin;
       if (!(any_a && any_b)) continue;  // no rank computes or broadcasts in this step
       size_t need = 0;
       if (a_stg || Pc > 1) need += *std::max_element(per_r.begin(), per_r.end());
@@ -359,8 +366,8 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
       // windows ramp up geometrically (1, 2, 4, ... W steps): the panels of window n+1 travel while window n computes,
       // so only the first, single-step window is exposed; a full-size second window had its whole broadcast in the
       // open (block-sparse config 3 on 4 GPUs: 11 of 55 ms, profiles/r02_trace_C3_n4_before_ramp.log)
-      const int wcap = nwin < 30 ? std::min(W, 1 << nwin) : W;
-      if (cnt > 0 && (cnt >= wcap || gbytes + need > kMaxWindowBytes)) { ++nwin; cnt = 0; gbytes = 0; win_of_k[k] = nwin; }
+      const int wcap = (pass == 0 && nwin < 30) ? std::min(W, 1 << nwin) : W;
+      if (cnt > 0 && (cnt >= wcap || gbytes + need > kMaxWindowBytes)) { ++nwin; cnt = 0; gbytes = 0; wmap[k] = nwin; }
       ++cnt; gbytes += need;
     }
   }
@@ -414,7 +421,7 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
       if (bs.bcast_a || (a_stg && bs.compute)) need += bs.a_elems * 8;
       const bool b_to_cache = b_cache && (bs.st->bcast_b || b_stg);
       if (!b_to_cache && (bs.bcast_b || (b_stg && bs.compute))) need += bs.b_elems * 8;
-      const int gw = win_of_k[bs.st->k];
+      const int gw = (b == 0 ? win_of_k : win_of_k_steady)[bs.st->k];
       if (!cur.steps.empty() && gw != cur_win) { bwins[b].push_back(std::move(cur)); cur = Window(); }
       cur_win = gw;
       cur.steps.push_back(x); cur.bytes += need;
