@@ -295,3 +295,26 @@ def test_summa_contract_exact_int_sparse(grid):
     assert npairs_c == npairs
     for key, t in out.items():
         assert np.array_equal(out_c[key], t)
+
+
+def test_screening_zero_pattern_is_order_insensitive_away_from_threshold():
+    """The result shape of a contraction is an fp32 norm product (sparse_shape.h:1589-1663). The engine and this
+    oracle sum k sequentially with individually rounded operations; the reference calls a vendor SGEMM whose
+    summation order is unspecified, so values agree only to rounding (the reference's own test pins 1e-4 %,
+    tests/sparse_shape.cpp:1478-1611). What matters downstream is the ZERO PATTERN (which result tiles exist): for
+    shapes whose non-zero products are well separated from the threshold — any realistic tile norm — every summation
+    order, and exact arithmetic, gives the same pattern. (INTEGRATION.md §5 documents the remaining difference:
+    products within a few ulp of the threshold.)"""
+    rng = np.random.default_rng(12)
+    thr = np.float32(O.FLT_EPSILON)
+    for trial in range(20):
+        Mt, Nt, Kt = (int(x) for x in rng.integers(3, 40, 3))
+        a = np.where(rng.random((Mt, Kt)) < 0.3, rng.uniform(1e-3, 10.0, (Mt, Kt)), 0.0).astype(np.float32)
+        b = np.where(rng.random((Kt, Nt)) < 0.3, rng.uniform(1e-3, 10.0, (Kt, Nt)), 0.0).astype(np.float32)
+        ksz = rng.integers(1, 600, Kt).astype(np.float32)
+        seq = O.shape_gemm_kernel(a, b, ksz, np.float32(1.0))                       # the engine's order
+        exact = (a.astype(np.float64) * ksz) @ (b.astype(np.float64) * ksz[:, None])  # any order, no rounding
+        rev = O.shape_gemm_kernel(a[:, ::-1].copy(), b[::-1].copy(), ksz[::-1].copy(), np.float32(1.0))  # reversed k
+        pat = seq >= thr
+        assert np.array_equal(pat, exact >= float(thr)) and np.array_equal(pat, rev >= thr)
+        assert np.allclose(seq, exact, rtol=1e-5)
