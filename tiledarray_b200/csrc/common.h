@@ -64,7 +64,11 @@ struct tadev_ctx {
   ncclComm* col_comm = nullptr;  // ranks sharing my grid column (B row-panels travel here)
   int rank = 0, nranks = 1, Pr = 1, Pc = 1, my_r = 0, my_c = 0;
   // grouped-GEMM launch policy
-  int gemm_sm_reserve = 0;          // SMs left free by the persistent kernel (for NCCL's CTAs)
+  int gemm_sm_reserve = 0;          // SMs the persistent kernel leaves free right now (for NCCL's CTAs)
+  int sm_reserve_thin = 0;          // ... for contractions whose panel traffic is small next to their GEMM work (dense)
+  int sm_reserve_wide = 0;          // ... for traffic-heavy (block-sparse) contractions: wide communicators, more CTAs
+  ncclComm* row_comm_wide = nullptr;
+  ncclComm* col_comm_wide = nullptr;
   bool force_generic_gemm = false;  // TADEV_GEMM_GENERIC=1: always use the cp.async kernel
   void* tmap_cache = nullptr;       // TmapCache (gemm_f64_ws.cu): per-tile CUtensorMaps in device memory
 };

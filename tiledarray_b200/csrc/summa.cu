@@ -56,6 +56,7 @@ extern "C" int tadev_comm_init(tadev_ctx* ctx, const void* unique_id128, int ran
   // panel broadcasts of window w+1 are always resident next to the GEMM of window w.
   ctx->gemm_sm_reserve = (Pr * Pc > 1) ? 4 : 0;
   if (const char* e = getenv("TADEV_SM_RESERVE")) ctx->gemm_sm_reserve = atoi(e);
+  ctx->sm_reserve_thin = ctx->gemm_sm_reserve;
   ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
   if (ctx->gemm_sm_reserve > 0) { cfg.minCTAs = 1; cfg.maxCTAs = ctx->gemm_sm_reserve; }
   // NCCL's default on sm_90+ launches its CTAs as thread-block clusters of 4, which must be co-scheduled inside
@@ -71,16 +72,29 @@ extern "C" int tadev_comm_init(tadev_ctx* ctx, const void* unique_id128, int ran
   ctx->my_c = in_grid ? rank % Pc : -1;
   TADEV_CHECK_NCCL(ncclCommSplit(ctx->world, in_grid ? ctx->my_r : NCCL_SPLIT_NOCOLOR, ctx->my_c, &ctx->row_comm, &cfg));
   TADEV_CHECK_NCCL(ncclCommSplit(ctx->world, in_grid ? ctx->my_c : NCCL_SPLIT_NOCOLOR, ctx->my_r, &ctx->col_comm, &cfg));
+  // A second, "wide" pair of communicators for contractions whose panel traffic is large next to their GEMM work
+  // (block-sparse config 3 at 8 GPUs receives 1.7 GB per rank against 20 ms of GEMM; 4 CTAs sustain 90-150 GB/s and
+  // left the GEMM waiting: share of the step 0.62). Those contractions leave `sm_reserve_wide` SMs to NCCL instead.
+  ctx->sm_reserve_wide = ctx->sm_reserve_thin > 0 ? 12 : 0;
+  if (const char* e = getenv("TADEV_SM_RESERVE_WIDE")) ctx->sm_reserve_wide = atoi(e);
+  if (ctx->sm_reserve_wide > ctx->sm_reserve_thin) {
+    ncclConfig_t wcfg = cfg;
+    wcfg.minCTAs = 1; wcfg.maxCTAs = ctx->sm_reserve_wide;
+    TADEV_CHECK_NCCL(ncclCommSplit(ctx->world, in_grid ? ctx->my_r : NCCL_SPLIT_NOCOLOR, ctx->my_c, &ctx->row_comm_wide, &wcfg));
+    TADEV_CHECK_NCCL(ncclCommSplit(ctx->world, in_grid ? ctx->my_c : NCCL_SPLIT_NOCOLOR, ctx->my_r, &ctx->col_comm_wide, &wcfg));
+  }
   return TADEV_OK;
 }
 
 extern "C" int tadev_comm_destroy(tadev_ctx* ctx) {
   if (!ctx) return TADEV_OK;
+  if (ctx->row_comm_wide) { ncclCommDestroy(ctx->row_comm_wide); ctx->row_comm_wide = nullptr; }
+  if (ctx->col_comm_wide) { ncclCommDestroy(ctx->col_comm_wide); ctx->col_comm_wide = nullptr; }
   if (ctx->row_comm) { ncclCommDestroy(ctx->row_comm); ctx->row_comm = nullptr; }
   if (ctx->col_comm) { ncclCommDestroy(ctx->col_comm); ctx->col_comm = nullptr; }
   if (ctx->world) { ncclCommDestroy(ctx->world); ctx->world = nullptr; }
   ctx->rank = 0; ctx->nranks = 1; ctx->Pr = ctx->Pc = 1; ctx->my_r = ctx->my_c = 0;
-  ctx->gemm_sm_reserve = 0;
+  ctx->gemm_sm_reserve = ctx->sm_reserve_thin = ctx->sm_reserve_wide = 0;
   return TADEV_OK;
 }
 
@@ -528,6 +542,32 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
 
   const auto host_t0 = std::chrono::steady_clock::now();
   auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+  // ---- which communicators: contractions whose panel traffic is large next to their GEMM work (block-sparse ones)
+  //      use the wide pair and leave more SMs to NCCL; the decision uses replicated data only (every rank agrees).
+  //      Estimate: bytes the busiest rank receives at ~100 GB/s (4 CTAs) vs its GEMM work at ~35 TFLOP/s.
+  bool wide = false;
+  if (multi && ctx->row_comm_wide && ctx->col_comm_wide) {
+    double a_bytes = 0, b_bytes = 0, gflop = 0;
+    for (int k = 0; k < Kt; ++k) {
+      double na = 0, nbk = 0;
+      for (int i = 0; i < Mt; ++i) if (!P.a_norms || P.a_norms[(size_t)i * Kt + k] >= P.threshold) na += (double)P.m_ext[i];
+      for (int j = 0; j < Nt; ++j) if (!P.b_norms || P.b_norms[(size_t)k * Nt + j] >= P.threshold) nbk += (double)P.n_ext[j];
+      a_bytes += na * (double)P.k_ext[k] * 8.0; b_bytes += nbk * (double)P.k_ext[k] * 8.0;
+      gflop += 2.0 * na * nbk * (double)P.k_ext[k];
+    }
+    const double recv = (a_bytes / Pr) * (Pc - 1) / Pc + (b_bytes / Pc) * (Pr - 1) / Pr;
+    const double t_comm = recv / 100e9, t_gemm = gflop / ((double)Pr * Pc * 35e12);
+    wide = t_comm > 0.5 * t_gemm;
+    if (const char* e = getenv("TADEV_WIDE_COMM")) wide = atoi(e) != 0;
+  }
+  ncclComm* const row_comm = wide ? ctx->row_comm_wide : ctx->row_comm;
+  ncclComm* const col_comm = wide ? ctx->col_comm_wide : ctx->col_comm;
+  struct ReserveGuard {  // the GEMM launchers of this contraction leave the matching number of SMs free
+    tadev_ctx* ctx; int saved;
+    ~ReserveGuard() { ctx->gemm_sm_reserve = saved; }
+  } reserve_guard{ctx, ctx->gemm_sm_reserve};
+  if (multi) ctx->gemm_sm_reserve = wide ? ctx->sm_reserve_wide : ctx->sm_reserve_thin;
+
   SummaWindows X;
   build_summa_windows(Pr, Pc, r, c, P, X);
   SummaSchedule& S = X.S;
@@ -636,8 +676,8 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
       *flag = local_rc;
       TADEV_CHECK_CUDA(cudaMemcpyAsync(dflag, flag, sizeof(int32_t), cudaMemcpyHostToDevice, sc));
       // every rank of the grid is in one row and one column communicator: max over both = max over the grid
-      ncclResult_t n1 = ncclAllReduce(dflag, dflag, 1, ncclInt32, ncclMax, ctx->row_comm, sc);
-      ncclResult_t n2 = n1 == ncclSuccess ? ncclAllReduce(dflag, dflag, 1, ncclInt32, ncclMax, ctx->col_comm, sc) : n1;
+      ncclResult_t n1 = ncclAllReduce(dflag, dflag, 1, ncclInt32, ncclMax, row_comm, sc);
+      ncclResult_t n2 = n1 == ncclSuccess ? ncclAllReduce(dflag, dflag, 1, ncclInt32, ncclMax, col_comm, sc) : n1;
       if (n2 != ncclSuccess) { cudaFreeHost(flag); tadev_set_error("tadev_summa_f64: status all-reduce failed: %s", ncclGetErrorString(n2)); return TADEV_ENCCL; }
       TADEV_CHECK_CUDA(cudaMemcpyAsync(flag, dflag, sizeof(int32_t), cudaMemcpyDeviceToHost, sc));
       TADEV_CHECK_CUDA(cudaStreamSynchronize(sc));
@@ -651,7 +691,8 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
     }
   } else if (local_rc) return local_rc;
   static const bool trace_host = getenv("TADEV_SUMMA_TRACE") && atoi(getenv("TADEV_SUMMA_TRACE"));
-  if (trace_host) fprintf(stderr, "[tadev summa rank %d] host: schedule+windows+resources ready at %.3f ms\n", ctx->rank, host_ms());
+  if (trace_host) fprintf(stderr, "[tadev summa rank %d] host: schedule+windows+resources ready at %.3f ms (%s communicators, %d SMs left to NCCL)\n",
+                          ctx->rank, host_ms(), wide ? "wide" : "thin", ctx->gemm_sm_reserve);
   TADEV_CHECK_CUDA(cudaEventRecord(ev_start, s0));
   TADEV_CHECK_CUDA(cudaStreamWaitEvent(sc, ev_start, 0));
   TADEV_CHECK_CUDA(cudaStreamWaitEvent(sh, ev_start, 0));
@@ -908,12 +949,12 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
         // same (communicator, k) order on every rank of a group => no cross-communicator deadlock
         if (!row_bcasts.empty()) {
           TADEV_CHECK_NCCL(ncclGroupStart());
-          for (auto& bc : row_bcasts) TADEV_CHECK_NCCL(ncclBroadcast(bc.ptr, bc.ptr, bc.bytes, ncclChar, bc.root, ctx->row_comm, sc));
+          for (auto& bc : row_bcasts) TADEV_CHECK_NCCL(ncclBroadcast(bc.ptr, bc.ptr, bc.bytes, ncclChar, bc.root, row_comm, sc));
           TADEV_CHECK_NCCL(ncclGroupEnd());
         }
         if (!col_bcasts.empty()) {
           TADEV_CHECK_NCCL(ncclGroupStart());
-          for (auto& bc : col_bcasts) TADEV_CHECK_NCCL(ncclBroadcast(bc.ptr, bc.ptr, bc.bytes, ncclChar, bc.root, ctx->col_comm, sc));
+          for (auto& bc : col_bcasts) TADEV_CHECK_NCCL(ncclBroadcast(bc.ptr, bc.ptr, bc.bytes, ncclChar, bc.root, col_comm, sc));
           TADEV_CHECK_NCCL(ncclGroupEnd());
         }
       }
