@@ -136,8 +136,8 @@ def _cpu_plan(config, n, tile):
             Cz &= A
         e = [tt] * nt
         return f"block-sparse N={nn} tile={tt} 10%", e, e, e, 0, 0, A, B, Cz
-    if config in ("C4", "C4r"):
-        v = 800 if config == "C4" else 256
+    if config in ("C4", "C4h", "C4r"):
+        v = {"C4": 800, "C4h": 400, "C4r": 256}[config]
         o1, v1 = example_tiling(100, 64).extents, example_tiling(v, 64).extents
         oo = [x * y for x in o1 for y in o1]
         vv = [x * y for x in v1 for y in v1]
@@ -247,7 +247,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="tadev", choices=["tadev", "reference"])
-    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C3m", "C4", "C4r", "C5", "C5r"],
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C3m", "C4", "C4h", "C4r", "C5", "C5r"],
                     help="BASELINE.json config (default C2 = configs[1], the headline); C4r/C5r are reduced variants")
     ap.add_argument("--n", type=int, default=None)
     ap.add_argument("--tile", type=int, default=None)

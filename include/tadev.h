@@ -257,6 +257,11 @@ int tadev_plan_general_product(const char* target, const char* left, const char*
  * row/column tile broadcasts (:712,:849,:903) by NCCL broadcasts of packed panels on
  * row/column communicators of a Pr x Pc grid (one process per GPU). */
 int tadev_comm_unique_id(void* out128);
+/* Creates the world communicator and, by splitting it, a THIN and a WIDE pair of row / column communicators for the
+ * Pr x Pc grid (rank r*Pc + c sits at grid position (r, c); ranks >= Pr*Pc stay outside). NCCL is configured without
+ * thread-block clusters (cgaClusterSize = 1) and capped to the SMs the persistent GEMM leaves free: 4 for the thin pair
+ * (TADEV_SM_RESERVE), 12 for the wide pair (TADEV_SM_RESERVE_WIDE) that tadev_summa_f64 picks for contractions whose
+ * panel traffic is large next to their GEMM work (block-sparse; TADEV_WIDE_COMM=0/1 forces the choice). */
 int tadev_comm_init(tadev_ctx* ctx, const void* unique_id128, int rank, int nranks, int Pr, int Pc);
 int tadev_comm_destroy(tadev_ctx* ctx);
 /* Point-to-point redistribution of tiles over the world communicator: this rank sends nsend tiles and

@@ -19,7 +19,7 @@ GemmTimingHook& tadev_gemm_timing_hook() {
   static thread_local GemmTimingHook hook;
   return hook;
 }
-extern "C" const char* tadev_version(void) { return "tadev 0.1 (sm_100a)"; }
+extern "C" const char* tadev_version(void) { return "tadev 0.2 (sm_100a)"; }
 
 extern "C" int tadev_device_count(int* n) {
   TADEV_REQUIRE(n, "tadev_device_count: null out");

@@ -358,6 +358,18 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
   // Two maps: block 0 ramps its windows up (pipeline fill); later row blocks of a host-resident / lazy-operand
   // contraction start with their first panels already prefetched during the previous block, so they use full-size
   // windows from the start (the ramp cost ~15 % per block: profiles/r02_trace_C2_n8_e2e_depth2.log).
+  double a_block_frac = 1.0;  // largest share of this grid row's tile rows that one row block holds
+  if (nb > 1 && !my_rows.empty()) {
+    const int L = (int)my_rows.size();
+    const int64_t wtot = c_host && nb >= 2 ? 2 * (int64_t)nb - 1 : nb, wsc = c_host && nb >= 2 ? 2 : 1;
+    int most = 1;
+    for (int b = 0; b < nb; ++b) {
+      const int lo = (int)((int64_t)L * std::min<int64_t>(wsc * b, wtot) / wtot), hi = (int)((int64_t)L * std::min<int64_t>(wsc * (b + 1), wtot) / wtot);
+      most = std::max(most, hi - lo);
+    }
+    // every grid row cuts its rows the same way; one extra row of slack for rounding between grid rows
+    a_block_frac = std::min(1.0, (double)(most + 1) / (double)std::max(1, (Mt + Pr - 1) / Pr));
+  }
   std::vector<int> win_of_k(std::max(Kt, 1), 0), win_of_k_steady(std::max(Kt, 1), 0);
   for (int pass = 0; pass < 2; ++pass) {
     std::vector<int>& wmap = pass == 0 ? win_of_k : win_of_k_steady;
@@ -375,7 +387,9 @@ void build_summa_windows(int Pr, int Pc, int r, int c, const tadev_summa_plan& P
       wmap[k] = nwin;
       if (!(any_a && any_b)) continue;  // no rank computes or broadcasts in this step
       size_t need = 0;
-      if (a_stg || Pc > 1) need += *std::max_element(per_r.begin(), per_r.end());
+      // (with row blocks the ring holds only one block's rows of an A panel: BASELINE config 4 has 22.7 GB A panels but
+      // 2.3 GB per row block - without this factor its windows degenerated to single steps, K = 4096 per work item)
+      if (a_stg || Pc > 1) need += (size_t)((double)*std::max_element(per_r.begin(), per_r.end()) * a_block_frac);
       if ((b_stg || Pr > 1) && !b_cache) need += *std::max_element(per_c.begin(), per_c.end());
       // windows ramp up geometrically (1, 2, 4, ... W steps): the panels of window n+1 travel while window n computes,
       // so only the first, single-step window is exposed; a full-size second window had its whole broadcast in the
