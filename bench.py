@@ -72,7 +72,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def measure_gemm_traffic(args, max_launches=20, timeout_s=420):
+def measure_gemm_traffic(args, max_launches=20, timeout_s=180):
     """DRAM bytes per launch of the GEMM kernel, measured IN THIS RUN: a child `ncu` profiles the same command line
     (one step, no warm-up, no e2e / CPU legs) for dram__bytes_read.sum + dram__bytes_write.sum of up to
     `max_launches` launches of gemm_grouped_f64_ws_kernel and the mean per launch is reported (counters, not timings:
@@ -80,6 +80,8 @@ def measure_gemm_traffic(args, max_launches=20, timeout_s=420):
     import csv
     import io
     import shutil
+    if any(k.startswith(("NV_NSIGHT", "CUDA_INJECTION", "NV_COMPUTE_PROFILER", "NSYS_")) for k in os.environ):
+        return None, "this process is itself running under a profiler: no nested ncu"
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
         return None, "ncu not found"

@@ -404,3 +404,25 @@ def test_tiledarray_shim_type_checks():
                           "-I", os.path.join(ROOT, "tests", "cpp", "ta_facsimile"),
                           os.path.join(ROOT, "tests", "cpp", "test_shim_syntax.cpp")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-3000:]
+
+
+def test_summa_windows_config4_row_blocks_and_ramp(lib):
+    """Window policy of the driver on BASELINE config 4's structure (lazy left operand => result in row blocks, B
+    cached after the first block, 8x1 grid): windows ramp up 1, 2, 2, ... steps, and they are cut by the ROW BLOCK's
+    share of an A panel (22.7 GB per step for the whole panel, 2.3 GB per block), not by the whole panel — with the
+    whole-panel bound every window degenerated to a single step (1690 instead of 850 launches on one GPU)."""
+    from tiledarray_b200 import _lib as L
+    v = [64] * 12 + [32]
+    o = [64, 36]
+    m_ext = [x * y for x in v for y in v]      # fused (a,b): 169 tile rows of V
+    k_ext = list(m_ext)                        # fused (c,d)
+    n_ext = [x * y for x in o for y in o]      # fused (i,j): 4 tile columns
+    Pr, Pc = 8, 1
+    t = _comm_trace(lib, Pr, Pc, 3, 0, m_ext, n_ext, k_ext, None, None, None, L.SUMMA_A_LAZY, 0, 0)
+    cols = [(g, k) for (cm, g, k, root, nb) in t if cm == 1]   # column-communicator broadcasts (B panels), block 0 only
+    groups = sorted({g for g, _ in cols})
+    # one broadcast per (window, root row): 169 steps in windows of 1, 2, 2, 2, ... => 85 windows
+    assert len(groups) == 85, len(groups)
+    assert sum(1 for g, _ in cols if g == groups[0]) == 1          # first window: a single step, one root
+    assert sum(1 for g, _ in cols if g == groups[1]) == 2          # then two steps = two roots per window
+    assert not [x for x in t if x[0] == 0]                          # Pc == 1: A panels never travel
