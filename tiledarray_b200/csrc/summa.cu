@@ -547,7 +547,7 @@ extern "C" int tadev_summa_f64(tadev_ctx* ctx, const tadev_summa_plan* plan, tad
   TADEV_REQUIRE((!a_lazy || P.a_provider) && (!b_lazy || P.b_provider), "tadev_summa_f64: lazy operand without a tile provider");
   // "staged" operands have no device-resident tiles: every panel is materialised in the ring (or the
   // B cache) by an upload or by the provider, on the staging stream
-  const bool a_stg = a_host || a_lazy, b_stg = b_host || b_lazy;
+  const bool b_stg = b_host || b_lazy;
   TADEV_CHECK_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s0 = ctx->streams[0];                       // compute
   cudaStream_t sd = ctx->streams[ctx->streams.size() > 1 ? 1 : 0];  // result download

@@ -17,9 +17,9 @@ namespace {
 
 constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 4, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
 
-// exclusive scan of one 4096-element block (in place allowed); block_sums[blockIdx.x] = block total
-__global__ void __launch_bounds__(SCAN_THREADS) tl_scan_block_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
-                                                                     int32_t* __restrict__ block_sums, int64_t n) {
+// exclusive scan of one 4096-element block; block_sums[blockIdx.x] = block total. `in` and `out` may be the same
+// array (the callers scan in place), hence no __restrict__: every element is read and later written by one thread.
+__global__ void __launch_bounds__(SCAN_THREADS) tl_scan_block_kernel(const int32_t* in, int32_t* out, int32_t* block_sums, int64_t n) {
   __shared__ int32_t warp_sums[32];
   const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
   int32_t v[SCAN_ITEMS];
