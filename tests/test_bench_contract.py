@@ -27,3 +27,16 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_every_config():
+    """`bench.py --impl reference --config Cx`: the CPU arm exists for every BASELINE config (block-sparse pattern of
+    config 3 incl. the masked variant, the T,T op flags of config 4 as the reference plans it, config 5's fused 1024^3
+    tile GEMMs) and reports the sample it timed."""
+    for cfg, word in (("C3", "block-sparse"), ("C3m", "block-sparse"), ("C5", "permuted 4-index"), ("C1", "dense")):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", cfg, "--steps", "1",
+                              "--warmup", "0", "--cpu-budget", "0.5"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert out.returncode == 0, (cfg, out.stderr[-2000:])
+        d = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][0])
+        assert d["impl"] == "reference" and d["value"] > 0 and word in d["config"]["workload"] and cfg in d["config"]["workload"]
+        assert "tile pairs" in d["cpu_baseline"]["sample"]
