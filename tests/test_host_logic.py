@@ -336,7 +336,7 @@ def test_cpp_host_api(lib):
     assert out.returncode == 0 and "HOST API TESTS PASSED" in out.stdout, out.stdout + out.stderr
 
 
-def test_contraction_layout_named_configs():
+def test_contraction_layout_named_configs(lib):
     """tadev_contraction_layout: where SUMMA wants every operand tile (fused GEMM-side position, ProcGrid) for the
     BASELINE expressions: plain matrix product, config 4 (operands exchanged: R[ab,ij] = V[ab,cd] T[cd,ij]) and
     config 5 (both operands explicitly permuted: A -> (i,a | c,k), B -> (c,k | j,b))."""
