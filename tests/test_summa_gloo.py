@@ -155,3 +155,83 @@ def test_summa_two_ranks_gloo(case):
     assert ret["grid"] == (g.proc_rows, g.proc_cols)
     if len(case[2]) == 1:
         assert ret["grid"] == (2, 1)  # both grid orientations are exercised by CASES
+
+
+def _plan_worker(rank, world_size, port, case, ret):
+    """Play the EXACT broadcast plan tadev_summa_f64 would issue (tadev_summa_comm_trace: one broadcast per window,
+    communicator and root, in issue order) with gloo broadcasts on a 2x2 grid. A rank-dependent plan (different call
+    order, different byte counts, a missing call) hangs or fails the size check; receivers verify the root's signature."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from tiledarray_b200 import _lib
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    lib = _lib.load()
+    m_ext, k_ext, n_ext, density, seed, flags, row_blocks = case
+    Mt, Kt, Nt = len(m_ext), len(k_ext), len(n_ext)
+    Pr, Pc = 2, 2
+    r, c = rank // Pc, rank % Pc
+    rng = np.random.default_rng(seed)
+    if density < 1.0:
+        a_n = (rng.random((Mt, Kt)) < density).astype(np.float32)
+        b_n = (rng.random((Kt, Nt)) < density).astype(np.float32)
+        c_n = ((a_n @ b_n) > 0).astype(np.float32)
+    else:
+        a_n = b_n = c_n = None
+    sp = _lib.SummaPlanC()
+    sp.Mt, sp.Nt, sp.Kt = Mt, Nt, Kt
+    keep = [np.asarray(x, dtype=np.int64) for x in (m_ext, n_ext, k_ext)]
+    sp.m_ext, sp.n_ext, sp.k_ext = (x.ctypes.data_as(C.POINTER(C.c_int64)) for x in keep)
+    if a_n is not None:
+        sp.a_norms, sp.b_norms, sp.c_norms = (x.ctypes.data_as(C.POINTER(C.c_float)) for x in (a_n, b_n, c_n))
+    sp.threshold = 0.5
+    sp.flags, sp.row_blocks = flags, row_blocks
+    n = C.c_int64()
+    _lib.check(lib.tadev_summa_comm_trace(Pr, Pc, r, c, C.byref(sp), None, None, None, None, None, 0, C.byref(n)))
+    cap = max(n.value, 1)
+    comm, group, kk, root, nbytes = ((C.c_int32 * cap)(), (C.c_int32 * cap)(), (C.c_int32 * cap)(), (C.c_int32 * cap)(), (C.c_int64 * cap)())
+    _lib.check(lib.tadev_summa_comm_trace(Pr, Pc, r, c, C.byref(sp), comm, group, kk, root, nbytes, cap, C.byref(n)))
+    row_groups = [dist.new_group([rr * Pc + cc for cc in range(Pc)]) for rr in range(Pr)]
+    col_groups = [dist.new_group([rr * Pc + cc for rr in range(Pr)]) for cc in range(Pc)]
+    ncalls, moved = 0, 0
+    for x in range(n.value):
+        which, k, rt, nb = comm[x], kk[x], root[x], nbytes[x]
+        grp = row_groups[r] if which == 0 else col_groups[c]
+        src = r * Pc + rt if which == 0 else rt * Pc + c   # world rank of the root inside my row / column
+        words = max(1, min(int(nb) // 8, 4096))             # a scaled-down payload of the same call
+        sig = float(which * 1000003 + k * 1009 + rt * 31) + float(nb % 9973)
+        t = torch.full((words,), sig, dtype=torch.float64) if rank == src else torch.zeros(words, dtype=torch.float64)
+        dist.broadcast(t, src, group=grp)
+        assert bool((t == sig).all()), (rank, x, which, k, rt, nb)
+        ncalls += 1
+        moved += int(nb)
+    gathered = [None] * world_size
+    dist.all_gather_object(gathered, (ncalls, moved))
+    if rank == 0:
+        ret["ok"] = True
+        ret["calls"] = [g[0] for g in gathered]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+PLAN_CASES = [
+    # (m_ext, k_ext, n_ext, density, seed, plan flags, row_blocks)
+    ([64] * 6, [64] * 9, [64] * 5, 1.0, 1, 0, 0),                     # dense, device-resident
+    ([64] * 7, [32] * 40, [64] * 6, 0.3, 2, 0, 0),                    # block-sparse, many steps: ramped windows of merged panels
+    ([64] * 8, [64] * 10, [64] * 6, 1.0, 3, 1 | 2 | 4, 0),            # host-resident operands and result: row blocks, B cache, depth 3
+    ([64] * 8, [64] * 10, [64] * 6, 0.5, 4, 8, 3),                    # lazy left operand, three row blocks, block-sparse
+]
+
+
+@pytest.mark.parametrize("case", PLAN_CASES)
+def test_summa_broadcast_plan_four_ranks_gloo(case):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_plan_worker, args=(4, port, case, ret), nprocs=4, join=True)
+    assert ret.get("ok") is True, dict(ret)
+    assert all(n > 0 for n in ret["calls"]), ret["calls"]
